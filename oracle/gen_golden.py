@@ -1,0 +1,172 @@
+"""Generate tests/golden/*.npz by running the REFERENCE'S OWN Python from /root/reference on the CPU.
+
+TEST INFRASTRUCTURE ONLY.  Run in the build container (the GPU box has no /root/reference):
+
+    python -m oracle.gen_golden
+
+See oracle/ref_import.py for exactly what is real reference code and what is substituted.  The
+fixtures pin oracle/cpu_ops.py + oracle/registration_np.py (tests/test_oracle.py) and are the
+reference answers the CUDA path is compared with on the GPU box (tests/test_*_gpu.py).
+"""
+import os
+import tempfile
+
+import numpy as np
+import torch
+
+from . import ref_import as R
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def _scene(seq, frames, beams, az):
+    from pcseqlearning_b200.synthetic import generate_sequence, sequence_fxyz
+    b = generate_sequence(seq, num_frames=frames, num_beams=beams, num_azimuth=az)
+    f = sequence_fxyz(b)
+    seg = b["segmentation_label"]
+    return b, f, seg
+
+
+def gen_radius_graph():
+    gu = R.load("pcdet.models.model_utils.graph_utils")
+    _, f, seg = _scene(1, 3, 24, 700)
+    f = f[seg < 17]  # ground removed by label
+    cases = {}
+    for name, (radius, K, sort) in dict(r125=(1.25, 32, True), r075=(0.75, 32, True), r025=(0.25, 32, True),
+                                        nn05=(0.5, 1, True), unsorted=(0.75, 8, False)).items():
+        g = gu.RadiusGraph(runtime_cfg={}, model_cfg=dict(RADIUS=radius, MAX_NUM_NEIGHBORS=K, SORT_BY_DIST=sort,
+                                                          RELATIVE_KEY="fxyz"))
+        er, eq, _ = g(R.edict(fxyz=f.clone()), R.edict(fxyz=f.clone()))
+        cases[name + "_eref"] = er.numpy()
+        cases[name + "_equery"] = eq.numpy()
+        cases[name + "_cfg"] = np.array([radius, K, int(sort)], np.float64)
+    # cross-frame nearest neighbour, the way register_to_next_frame drives the graph (:107-137)
+    fr = f[:, 0].round().long()
+    a, b = f[fr == 0].clone(), f[fr == 2].clone()
+    g = gu.RadiusGraph(runtime_cfg={}, model_cfg=dict(RADIUS=2.5, MAX_NUM_NEIGHBORS=1, SORT_BY_DIST=True,
+                                                      RELATIVE_KEY="fxyz"))
+    g.radius = (2.5 ** 2 + 2 ** 2) ** 0.5
+    g.qmin[0] = 2
+    g.qmax[0] = 2
+    er, eq, _ = g(R.edict(fxyz=b), R.edict(fxyz=a))  # ref = frame 2, query = frame 0
+    cases["cross_eref"] = er.numpy()
+    cases["cross_equery"] = eq.numpy()
+    cases["cross_ref"] = b.numpy()
+    cases["cross_query"] = a.numpy()
+    cases["points"] = f.numpy()
+    np.savez_compressed(os.path.join(OUT, "radius_graph.npz"), **cases)
+    print("radius_graph.npz", f.shape, {k: v.shape for k, v in cases.items() if k.endswith("eref")})
+
+
+def gen_grid_sampling():
+    gs = R.load("pcdet.models.model_utils.grid_sampling")
+    ct = R.load("pcdet.models.registration.preprocessors.cluster_tracking")
+    from torch_scatter import scatter
+    _, f, seg = _scene(2, 3, 24, 700)
+    out = dict(points=f.numpy())
+    for name, size in dict(sub008=[0.08, 0.08, 0.08], lvl0=[0.4, 0.4, 0.6], lvl2=[0.1, 0.1, 0.15]).items():
+        s = gs.GridSampling3D(size)
+        sampled, inv = s(f.clone(), return_inverse=True)
+        out[name + "_sampled"] = sampled.numpy()
+        out[name + "_inv"] = inv.numpy()
+        out[name + "_size"] = np.array(size)
+    # the 0.08 m pick-one subsample of simple_reg.py:119-124
+    inv = torch.from_numpy(out["sub008_inv"])
+    out["sub008_pick"] = scatter(torch.arange(f.shape[0]), inv, dim_size=int(inv.max()) + 1, dim=0,
+                                 reduce="max").numpy()
+    # sample_frame (cluster_tracking.py:39-51) on one frame with synthetic components
+    fr0 = f[f[:, 0] == 0].clone()
+    rng = np.random.default_rng(5)
+    comp = torch.from_numpy(rng.integers(0, 40, fr0.shape[0]))
+    stat = torch.from_numpy(rng.random(fr0.shape[0]) < 0.3)
+    frame = R.edict(fxyz=fr0, stationary=stat, component=comp,
+                    frame=torch.zeros(fr0.shape[0], 1, dtype=torch.int32))
+    sf = ct.sample_frame(gs.GridSampling3D([0.2, 0.2, 0.3]), frame)
+    out.update(sf_in_fxyz=fr0.numpy(), sf_in_comp=comp.numpy(), sf_in_stat=stat.numpy(),
+               sf_fxyz=sf.fxyz.numpy(), sf_stat=sf.stationary.numpy(), sf_comp=sf.component.numpy(),
+               sf_frame=sf.frame.numpy())
+    np.savez_compressed(os.path.join(OUT, "grid_sampling.npz"), **out)
+    print("grid_sampling.npz", f.shape)
+
+
+def gen_proposal():
+    """ClusterProposal.propose_cluster (cluster_proposal.py:34-88) with the north-star yaml's GRAPH block."""
+    cp = R.load("pcdet.models.registration.preprocessors.cluster_proposal")
+    b, f, seg = _scene(4, 13, 24, 600)  # 13 frames -> two 10-frame chunks
+    keep = seg < 17
+    f = f[keep]
+    sweep = b["point_sweep"][keep]
+    keys = ["component_rad1x25", "component_rad0x75", "component_rad0x25"]
+    with tempfile.TemporaryDirectory() as d:
+        cfg = R.edict(GRAPH=dict(TYPE="RadiusGraph", RADIUS=[1.25, 0.75, 0.25], MAX_NUM_NEIGHBORS=32,
+                                 SORT_BY_DIST=True, RELATIVE_KEY="fxyz"), COMPONENT_KEYS=keys, DIR=d)
+        mod = cp.ClusterProposal(cfg, {})
+        seq = R.edict(point_fxyz=f.clone(), point_sweep=sweep.clone(), frame_id=b["frame_id"][0])
+        seq = mod.propose_cluster(seq)
+    out = dict(points=f.numpy(), sweep=sweep.numpy())
+    for k in keys:
+        out[k] = seq["point_" + k].numpy()
+    np.savez_compressed(os.path.join(OUT, "proposal.npz"), **out)
+    print("proposal.npz", f.shape, {k: int(out[k].max()) + 1 for k in keys})
+
+
+def gen_registration():
+    """register_to_next_frame (registration_utils.py:83-206) at the three levels of the yaml."""
+    gu = R.load("pcdet.models.model_utils.graph_utils")
+    gs = R.load("pcdet.models.model_utils.grid_sampling")
+    ru = R.load("pcdet.models.registration.preprocessors.registration_utils")
+    ct = R.load("pcdet.models.registration.preprocessors.cluster_tracking")
+    from . import cpu_ops as ops
+    b, f, seg = _scene(3, 4, 32, 900)
+    f = f[seg < 17].numpy()
+    comp, _ = ops.propose_clusters(f, 0.75)
+    fr = np.rint(f[:, 0]).astype(int)
+    out = {}
+    for case, (fa, fb) in dict(fwd=(0, 1), bwd=(2, 0)).items():
+        A, B = f[fr == fa], f[fr == fb]
+        cA = comp[fr == fa]
+        cA = cA - cA.min()
+        C = int(cA.max()) + 1
+        cB = comp[fr == fb]
+        # components with a large extent are "stationary" (cluster_tracking.py:860-861)
+        fa_pts = R.edict(fxyz=torch.from_numpy(A), component=torch.from_numpy(cA))
+        diamA = ct.component_diameter(fa_pts)[torch.from_numpy(cA)].numpy()
+        statA = diamA > 12.5
+        statB = np.zeros(B.shape[0], bool)
+        for lvl, (radius, vsz) in enumerate(zip([2.5, 1.25, 1.0], [[0.4, 0.4, 0.6], [0.2, 0.2, 0.3],
+                                                                   [0.1, 0.1, 0.15]])):
+            sampler = gs.GridSampling3D(vsz)
+            frameA = R.edict(fxyz=torch.from_numpy(A.copy()), stationary=torch.from_numpy(statA),
+                             component=torch.from_numpy(cA),
+                             frame=torch.full((A.shape[0], 1), fa, dtype=torch.int32))
+            frameB = R.edict(fxyz=torch.from_numpy(B.copy()), stationary=torch.from_numpy(statB),
+                             component=torch.from_numpy(cB),
+                             frame=torch.full((B.shape[0], 1), fb, dtype=torch.int32))
+            sA = ct.sample_frame(sampler, frameA)
+            sB = ct.sample_frame(sampler, frameB)
+            g = gu.RadiusGraph(runtime_cfg={}, model_cfg=dict(RADIUS=radius, MAX_NUM_NEIGHBORS=1,
+                                                              SORT_BY_DIST=True, RELATIVE_KEY="fxyz"))
+            pre = {k: sA[k].clone().numpy() for k in ["fxyz", "stationary", "component"]}
+            preB = {k: sB[k].clone().numpy() for k in ["fxyz", "stationary"]}
+            mv, T, l1, ratio = ru.register_to_next_frame(g, sA, sB, C, 10, max_iter=80, stopping_delta=0.05)
+            p = f"{case}_l{lvl}_"
+            out.update({p + "mov_fxyz": pre["fxyz"], p + "mov_stat": pre["stationary"],
+                        p + "mov_comp": pre["component"], p + "ref_fxyz": preB["fxyz"],
+                        p + "ref_stat": preB["stationary"], p + "C": np.array(C), p + "radius": np.array(radius),
+                        p + "T": T.numpy(), p + "l1": l1.numpy(), p + "ratio": ratio.numpy(),
+                        p + "moved": mv.fxyz.numpy()})
+    np.savez_compressed(os.path.join(OUT, "registration.npz"), **out)
+    print("registration.npz", {k: v.shape for k, v in out.items() if k.endswith("_T")})
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.manual_seed(0)
+    gen_radius_graph()
+    gen_grid_sampling()
+    gen_proposal()
+    gen_registration()
+
+
+if __name__ == "__main__":
+    main()
