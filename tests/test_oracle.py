@@ -114,7 +114,7 @@ def test_registration_matches_reference_python(golden_dir, case, lvl):
     assert ang.max() < 1e-4 and dt.max() < 1e-4
     np.testing.assert_allclose(l1, g[p + "l1"], rtol=0, atol=1e-4)
     np.testing.assert_allclose(ratio, g[p + "ratio"], rtol=0, atol=1e-6)
-    np.testing.assert_allclose(moved, g[p + "moved"], rtol=1e-5, atol=1e-4)  # fp32 coordinates at up to 75 m
+    np.testing.assert_allclose(moved, g[p + "moved"], rtol=0, atol=5e-4)  # reference centroids are fp32 sums in unspecified order: ~3e-4 m noise on 100 m-wide components
 
 
 def test_points_in_boxes():
