@@ -1,0 +1,128 @@
+/*
+ * pcseq_b200.h -- C ABI of libpcseq_b200.so, the sm_100a implementation of PCSeqLearning's
+ * cluster-extraction / tracking hot path.
+ *
+ * Conventions
+ *   - every entry point takes a CUDA stream (cudaStream_t passed as void*; NULL = legacy default
+ *     stream), plain device pointers and sizes; nothing here depends on torch;
+ *   - all buffers are caller-allocated device memory unless marked (host);
+ *   - return value: 0 on success, otherwise a cudaError_t / negative pcs error code;
+ *     pcs_last_error() gives the text.  No entry point synchronises the stream unless it says so;
+ *   - points are rows of 4 float32 (frame, x, y, z) = one 16-byte aligned float4 per point, the
+ *     `point_fxyz` layout of the reference (pcdet/models/registration/simple_reg.py:115-117).
+ *
+ * Each function names the reference interface it replaces (paths relative to the reference root).
+ */
+#ifndef PCSEQ_B200_H
+#define PCSEQ_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCS_ERR_BAD_ARG (-2)
+#define PCS_ERR_TABLE_FULL (-3)
+#define PCS_ERR_KEY_RANGE (-4)
+#define PCS_MAX_SEGMENTS 64
+#define PCS_MAX_K 32
+
+typedef void *pcs_stream_t;
+
+/* One slot of the open-addressing cell table (16 bytes, read with one 128-bit load). */
+typedef struct {
+  int64_t key;   /* linearised cell key (with the segment prefix), -1 = empty */
+  int32_t start; /* first row of the cell in the cell-sorted point array */
+  int32_t count; /* number of points in the cell */
+} pcs_slot_t;
+
+int pcs_version(void);
+const char *pcs_last_error(void);
+/* Number of kernels launched by this library since load / since the last reset (for bench.py's gpu_launches). */
+int64_t pcs_launch_count(void);
+void pcs_reset_launch_count(void);
+
+/* ---- grid geometry --------------------------------------------------------------------------
+ * Replaces the torch ops of RadiusGraph.build_graph that derive the voxel grid
+ * (pcdet/models/model_utils/graph_utils.py:169-176): min/max over ref U query, origin
+ * lo = min - 2*vs, dims = rint((max + 2*vs - lo)/vs) + 3, coordinates rint((p - lo)/vs) + 1.
+ *
+ * A "segment" is a group of frames that the reference processes in one RadiusGraph call (one
+ * 10-frame chunk in ClusterProposal.propose_cluster, cluster_proposal.py:63-67): segment id of a point
+ * = min(int(frame) / seg_div, n_seg - 1).  Every segment has its own origin/dims exactly as if the
+ * reference had been called on that chunk alone; all segments share one table (key prefix).
+ * bounds: uint32[n_seg][8] order-preserving encodings of (min f,x,y,z, max f,x,y,z). */
+int pcs_bounds_init(pcs_stream_t s, uint32_t *bounds, int n_seg);
+int pcs_bounds_update(pcs_stream_t s, const float *pts, int64_t n, int seg_div, int n_seg, uint32_t *bounds);
+/* vs (host): voxel size per dimension.  Writes seg_lo f32[n_seg][4], seg_dims i64[n_seg][4]. */
+int pcs_grid_params(pcs_stream_t s, const uint32_t *bounds, int n_seg, const float *vs, float *seg_lo,
+                    int64_t *seg_dims);
+/* Reference-exact voxel coordinates / linear keys of points (graph_utils.py:174-175 +
+ * torch_hash_kernel.cu:31-47 map2key); either output may be NULL.  Used by parity tests and by the
+ * torch_hash-compatible API. */
+int pcs_voxel_keys(pcs_stream_t s, const float *pts, int64_t n, int seg_div, int n_seg, const float *seg_lo,
+                   const int64_t *seg_dims, const float *vs, int64_t *coords /*[n][4]*/, int64_t *keys /*[n]*/);
+
+/* ---- voxel hash build -----------------------------------------------------------------------
+ * Replaces hash_insert_gpu (pcdet/ops/torch_hash/src/torch_hash_kernel.cu:54-91, 411-442) together
+ * with the key computation above.  Instead of a multimap with one slot per point, unique cell keys
+ * are hashed and the points are counting-sorted by cell:
+ *   table[H]        open addressing over unique cell keys (H = power of two)
+ *   sorted_pts[n]   float4 points grouped by cell, sorted_idx[n] their original row index
+ *   counters int32[4]: [0] number of occupied cells, [1] scatter cursor, [2] error flag, [3] unused
+ * The table must NOT be pre-filled; the call clears it. */
+int pcs_hash_build(pcs_stream_t s, const float *pts, int64_t n, int seg_div, int n_seg, const float *seg_lo,
+                   const int64_t *seg_dims, const float *vs, pcs_slot_t *table, int64_t H, float *sorted_pts,
+                   int32_t *sorted_idx, int32_t *counters);
+
+/* ---- neighbour search -----------------------------------------------------------------------
+ * Replaces radius_graph_gpu = count_radius_graph_degree_kernel + radius_graph_kernel
+ * (torch_hash_kernel.cu:224-409, 487-561) in ONE pass: for every query the cells
+ * [c + qmin, c + qmax] are looked up, candidates are filtered by the fp32 4-D distance test
+ * d2 <= r*r (same FMA order as the reference) and the K nearest are kept.
+ *   order      optional int32[m]: the i-th work item processes query order[i] (cell-coherent order)
+ *   radius     optional float[m] per-query radius; NULL -> radius_scalar
+ *   K          1..32 neighbours kept (the K smallest (d2, ref index) pairs; ties by ascending index)
+ *   nbr_idx    int32[m][K] reference row indices, ascending (d2, index); may be NULL when uf_parent set
+ *   nbr_d2     float[m][K] optional
+ *   nbr_cnt    int32[m] = min(#accepted, K)
+ *   uf_parent  optional int32[n_ref == m]: union-find forest; when given, every (query, neighbour)
+ *              pair is united in-kernel (fused connected components, no edge list materialised). */
+int pcs_radius_search(pcs_stream_t s, const pcs_slot_t *table, int64_t H, const float *sorted_pts,
+                      const int32_t *sorted_idx, int seg_div, int n_seg, const float *seg_lo,
+                      const int64_t *seg_dims, const float *vs, const float *queries, int64_t m,
+                      const int32_t *order, const int *qmin, const int *qmax, const float *radius,
+                      float radius_scalar, int K, int32_t *nbr_idx, float *nbr_d2, int32_t *nbr_cnt,
+                      int32_t *uf_parent);
+
+/* Exclusive scan int32 -> int64 with the grand total at out[n] (out has n+1 entries).
+ * Replaces `cumsum(degree) - degree` (torch_hash_kernel.cu:534-538) without the two blocking .item(). */
+int pcs_exclusive_scan(pcs_stream_t s, const int32_t *in, int64_t n, int64_t *out, void *tmp, int64_t tmp_bytes);
+int64_t pcs_exclusive_scan_tmp_bytes(int64_t n);
+
+/* Padded neighbour lists -> reference edge layout int64[E][2] rows (ref_idx, query_idx), grouped by
+ * ascending query (torch_hash_kernel.cu:395-399, 540-541).  dists float[E] optional. */
+int pcs_lists_to_edges(pcs_stream_t s, const int32_t *nbr_idx, const float *nbr_d2, const int32_t *nbr_cnt,
+                       const int64_t *offsets, int64_t m, int K, int64_t *edges, float *dists);
+
+/* ---- connected components -------------------------------------------------------------------
+ * Replaces graph_utils.connected_components (graph_utils.py:40-53: device->host copy + single-thread
+ * scipy.sparse.csgraph.connected_components) with a lock-free union-find on the device. */
+int pcs_uf_init(pcs_stream_t s, int32_t *parent, int64_t n);
+int pcs_uf_union_edges(pcs_stream_t s, int32_t *parent, const int64_t *e0, const int64_t *e1, int64_t E);
+/* Flatten + canonical numbering.  labels int64[n]: rank of the component's smallest member index
+ * among the components of the same segment (segment of node i = seg_of[i], NULL = one segment) plus
+ * the number of components in all earlier segments -- scipy's numbering applied chunk by chunk
+ * with a running offset (cluster_proposal.py:75-81).  n_comp int64[n_seg] per-segment counts.
+ * tmp: pcs_uf_labels_tmp_bytes(n, n_seg) bytes. */
+int pcs_uf_labels(pcs_stream_t s, int32_t *parent, int64_t n, const int32_t *seg_of, int n_seg, int64_t *labels,
+                  int64_t *n_comp, void *tmp, int64_t tmp_bytes);
+int64_t pcs_uf_labels_tmp_bytes(int64_t n, int n_seg);
+/* int32 segment id per point from the frame column (seg = min(int(frame)/seg_div, n_seg-1)). */
+int pcs_point_segments(pcs_stream_t s, const float *pts, int64_t n, int seg_div, int n_seg, int32_t *seg_of);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

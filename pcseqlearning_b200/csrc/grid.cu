@@ -1,0 +1,344 @@
+// grid.cu -- voxel grid geometry + open-addressing cell hash with counting sort (sm_100a).
+//
+// Replaces, for the cluster-tracking path, the torch ops of RadiusGraph.build_graph
+// (pcdet/models/model_utils/graph_utils.py:169-183) and hash_insert_gpu
+// (pcdet/ops/torch_hash/src/torch_hash_kernel.cu:54-91).  See include/pcseq_b200.h.
+#include "common.cuh"
+
+namespace pcs {
+
+thread_local char g_err[512] = "";
+long long g_launches = 0;
+
+int set_error(int code, const char *what) {
+  snprintf(g_err, sizeof(g_err), "%s (code %d%s%s)", what, code, code > 0 ? ": " : "",
+           code > 0 ? cudaGetErrorString((cudaError_t)code) : "");
+  return code;
+}
+
+int check_launch(const char *what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error((int)e, what);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// bounds: per-segment min/max of (frame, x, y, z)
+// ------------------------------------------------------------------------------------------------
+__global__ void bounds_init_kernel(unsigned int *bounds, int n_seg) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_seg * 8) bounds[i] = ((i & 7) < 4) ? 0xffffffffu : 0u;  // min slots = +max, max slots = 0
+}
+
+// One float4 per thread per step, grid-stride.  Lanes of a warp are grouped by segment with
+// match_any so each distinct segment costs 8 redux + 8 shared atomics per warp; blocks flush their
+// shared copy with global atomics once at the end.
+__global__ void __launch_bounds__(256) bounds_update_kernel(const float4 *__restrict__ pts, long long n,
+                                                            int seg_div, int n_seg,
+                                                            unsigned int *__restrict__ bounds) {
+  __shared__ unsigned int sb[PCS_MAX_SEGMENTS * 8];
+  for (int i = threadIdx.x; i < n_seg * 8; i += blockDim.x) sb[i] = ((i & 7) < 4) ? 0xffffffffu : 0u;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  long long nround = ((n + 31) / 32) * 32;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
+    bool valid = i < n;
+    float4 p = valid ? ldg_stream_f4(pts + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    int seg = valid ? point_segment(p.x, seg_div, n_seg) : -1;
+    unsigned int ox = f2ord(p.x), oy = f2ord(p.y), oz = f2ord(p.z), ow = f2ord(p.w);
+    unsigned int todo = __ballot_sync(0xffffffffu, valid);
+    while (todo) {
+      int leader = __ffs(todo) - 1;
+      int s = __shfl_sync(0xffffffffu, seg, leader);
+      bool mine = valid && (seg == s);
+      unsigned int grp = __ballot_sync(0xffffffffu, mine);
+      unsigned int mn0 = __reduce_min_sync(0xffffffffu, mine ? ox : 0xffffffffu);
+      unsigned int mn1 = __reduce_min_sync(0xffffffffu, mine ? oy : 0xffffffffu);
+      unsigned int mn2 = __reduce_min_sync(0xffffffffu, mine ? oz : 0xffffffffu);
+      unsigned int mn3 = __reduce_min_sync(0xffffffffu, mine ? ow : 0xffffffffu);
+      unsigned int mx0 = __reduce_max_sync(0xffffffffu, mine ? ox : 0u);
+      unsigned int mx1 = __reduce_max_sync(0xffffffffu, mine ? oy : 0u);
+      unsigned int mx2 = __reduce_max_sync(0xffffffffu, mine ? oz : 0u);
+      unsigned int mx3 = __reduce_max_sync(0xffffffffu, mine ? ow : 0u);
+      if (lane == leader) {
+        unsigned int *b = sb + s * 8;
+        atomicMin(b + 0, mn0);
+        atomicMin(b + 1, mn1);
+        atomicMin(b + 2, mn2);
+        atomicMin(b + 3, mn3);
+        atomicMax(b + 4, mx0);
+        atomicMax(b + 5, mx1);
+        atomicMax(b + 6, mx2);
+        atomicMax(b + 7, mx3);
+      }
+      todo &= ~grp;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_seg * 8; i += blockDim.x) {
+    if ((i & 7) < 4) {
+      if (sb[i] != 0xffffffffu) atomicMin(bounds + i, sb[i]);
+    } else {
+      if (sb[i] != 0u) atomicMax(bounds + i, sb[i]);
+    }
+  }
+}
+
+// lo = min - 2*vs ; hi = max + 2*vs ; dims = rint((hi - lo)/vs) + 3   (graph_utils.py:172-176, fp32)
+__global__ void grid_params_kernel(const unsigned int *__restrict__ bounds, int n_seg, float vs0, float vs1,
+                                   float vs2, float vs3, float *__restrict__ seg_lo,
+                                   long long *__restrict__ seg_dims) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_seg * 4) return;
+  int s = i >> 2, d = i & 3;
+  float vs = d == 0 ? vs0 : (d == 1 ? vs1 : (d == 2 ? vs2 : vs3));
+  unsigned int omin = bounds[s * 8 + d], omax = bounds[s * 8 + 4 + d];
+  if (omin == 0xffffffffu && omax == 0u) {  // empty segment
+    seg_lo[i] = 0.f;
+    seg_dims[i] = 1;
+    return;
+  }
+  float two_vs = __fmul_rn(vs, 2.0f);
+  float lo = __fsub_rn(ord2f(omin), two_vs);
+  float hi = __fadd_rn(ord2f(omax), two_vs);
+  seg_lo[i] = lo;
+  seg_dims[i] = (long long)rintf(__fdiv_rn(__fsub_rn(hi, lo), vs)) + 3;
+}
+
+__global__ void __launch_bounds__(256) voxel_keys_kernel(const float4 *__restrict__ pts, long long n, SegGeom g,
+                                                         long long *__restrict__ coords,
+                                                         long long *__restrict__ keys) {
+  __shared__ float4 s_lo[PCS_MAX_SEGMENTS];
+  __shared__ long long s_dims[PCS_MAX_SEGMENTS * 4];
+  load_geom(g, s_lo, s_dims);
+  __syncthreads();
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  long long c[4];
+  bool ovf;
+  long long k = point_key(pts[i], g, s_lo, s_dims, c, &ovf);
+  if (coords) {
+    coords[i * 4 + 0] = c[0];
+    coords[i * 4 + 1] = c[1];
+    coords[i * 4 + 2] = c[2];
+    coords[i * 4 + 3] = c[3];
+  }
+  if (keys) keys[i] = k & ((1LL << PCS_SEG_SHIFT) - 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// hash build: clear -> count (find-or-insert unique cell keys) -> assign ranges -> scatter
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) table_clear_kernel(int4 *__restrict__ table, long long H,
+                                                          int *__restrict__ counters) {
+  long long stride = (long long)gridDim.x * blockDim.x;
+  const int4 e = make_int4(-1, -1, 0, 0);  // key = -1, start = 0, count = 0
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < H; i += stride) table[i] = e;
+  if (blockIdx.x == 0 && threadIdx.x < 4) counters[threadIdx.x] = 0;
+}
+
+// find-or-insert; returns the slot.  Plain load first (most points land in an existing cell).
+__device__ __forceinline__ long long find_or_insert(pcs_slot_t *table, long long mask, long long key,
+                                                    int *counters) {
+  long long slot = hash_key(key) & mask;
+  for (long long probes = 0; probes <= mask; ++probes) {
+    long long cur = *((volatile long long *)&table[slot].key);
+    if (cur == key) return slot;
+    if (cur == PCS_EMPTY_KEY) {
+      unsigned long long prev = atomicCAS((unsigned long long *)&table[slot].key,
+                                          (unsigned long long)PCS_EMPTY_KEY, (unsigned long long)key);
+      if (prev == (unsigned long long)PCS_EMPTY_KEY) {
+        atomicAdd(&counters[0], 1);
+        return slot;
+      }
+      if ((long long)prev == key) return slot;
+    }
+    slot = (slot + 1) & mask;
+  }
+  atomicExch(&counters[2], PCS_ERR_TABLE_FULL);
+  return -1;
+}
+
+// Pass 1: count points per cell.  Lanes holding the same key are aggregated (match_any) so a warp of
+// spatially coherent points issues one probe sequence and one atomicAdd per distinct cell.
+__global__ void __launch_bounds__(256) hash_count_kernel(const float4 *__restrict__ pts, long long n, SegGeom g,
+                                                         pcs_slot_t *__restrict__ table, long long mask,
+                                                         int *__restrict__ counters) {
+  __shared__ float4 s_lo[PCS_MAX_SEGMENTS];
+  __shared__ long long s_dims[PCS_MAX_SEGMENTS * 4];
+  load_geom(g, s_lo, s_dims);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  long long nround = ((n + 31) / 32) * 32;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
+    bool valid = i < n;
+    long long key = -2 - lane;  // distinct dummies for inactive lanes
+    if (valid) {
+      long long c[4];
+      bool ovf;
+      key = point_key(ldg_stream_f4(pts + i), g, s_lo, s_dims, c, &ovf);
+      if (ovf) atomicExch(&counters[2], PCS_ERR_KEY_RANGE);
+    }
+    unsigned int peers = __match_any_sync(0xffffffffu, key);
+    int leader = __ffs(peers) - 1;
+    if (valid && lane == leader) {
+      long long slot = find_or_insert(table, mask, key, counters);
+      if (slot >= 0) atomicAdd(&table[slot].count, __popc(peers));
+    }
+  }
+}
+
+// Pass 2: give every occupied slot a contiguous row range.  Block-level scan of the counts, one
+// global atomic per block for the base (cell order in memory is arbitrary; nothing depends on it).
+__global__ void __launch_bounds__(256) assign_ranges_kernel(pcs_slot_t *__restrict__ table, long long H,
+                                                            int *__restrict__ counters) {
+  __shared__ int warp_tot[8];
+  __shared__ int block_base;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  long long base_i = (long long)blockIdx.x * (blockDim.x * 4) + threadIdx.x * 4;
+  int c[4];
+  int sum = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    long long i = base_i + k;
+    c[k] = (i < H) ? table[i].count : 0;
+    sum += c[k];
+  }
+  int incl = warp_incl_scan(sum, lane);
+  if (lane == 31) warp_tot[warp] = incl;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < 8; w++) {
+      int v = warp_tot[w];
+      warp_tot[w] = t;
+      t += v;
+    }
+    block_base = t > 0 ? atomicAdd(&counters[1], t) : 0;
+  }
+  __syncthreads();
+  int off = block_base + warp_tot[warp] + incl - sum;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    long long i = base_i + k;
+    if (i < H && c[k] > 0) table[i].start = off;  // start doubles as the scatter cursor in pass 3
+    off += c[k];
+  }
+}
+
+// Pass 3: scatter points into their cell ranges.  table[slot].start is advanced as a cursor; after the
+// pass start == first row + count, which pass 4 rewinds.
+__global__ void __launch_bounds__(256) hash_scatter_kernel(const float4 *__restrict__ pts, long long n, SegGeom g,
+                                                           pcs_slot_t *__restrict__ table, long long mask,
+                                                           float4 *__restrict__ sorted_pts,
+                                                           int *__restrict__ sorted_idx) {
+  __shared__ float4 s_lo[PCS_MAX_SEGMENTS];
+  __shared__ long long s_dims[PCS_MAX_SEGMENTS * 4];
+  load_geom(g, s_lo, s_dims);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  long long nround = ((n + 31) / 32) * 32;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
+    bool valid = i < n;
+    long long key = -2 - lane;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) {
+      long long c[4];
+      bool ovf;
+      p = ldg_stream_f4(pts + i);
+      key = point_key(p, g, s_lo, s_dims, c, &ovf);
+    }
+    unsigned int peers = __match_any_sync(0xffffffffu, key);
+    int leader = __ffs(peers) - 1;
+    int base = 0;
+    if (valid && lane == leader) {
+      long long slot = hash_key(key) & mask;
+      while (*((volatile long long *)&table[slot].key) != key) slot = (slot + 1) & mask;
+      base = atomicAdd(&table[slot].start, __popc(peers));
+    }
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (valid) {
+      int pos = base + __popc(peers & ((1u << lane) - 1));
+      sorted_pts[pos] = p;
+      sorted_idx[pos] = (int)i;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) rewind_ranges_kernel(pcs_slot_t *__restrict__ table, long long H) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < H) {
+    int c = table[i].count;
+    if (c > 0) table[i].start -= c;
+  }
+}
+
+}  // namespace pcs
+
+using namespace pcs;
+
+extern "C" {
+
+int pcs_version(void) { return 100; }
+const char *pcs_last_error(void) { return g_err; }
+int64_t pcs_launch_count(void) { return g_launches; }
+void pcs_reset_launch_count(void) { g_launches = 0; }
+
+int pcs_bounds_init(pcs_stream_t s, uint32_t *bounds, int n_seg) {
+  if (!bounds || n_seg < 1 || n_seg > PCS_MAX_SEGMENTS) return set_error(PCS_ERR_BAD_ARG, "pcs_bounds_init: bad args");
+  PCS_LAUNCH(bounds_init_kernel, 1, 512, 0, as_stream(s), bounds, n_seg);
+  return 0;
+}
+
+int pcs_bounds_update(pcs_stream_t s, const float *pts, int64_t n, int seg_div, int n_seg, uint32_t *bounds) {
+  if (!bounds || n_seg < 1 || n_seg > PCS_MAX_SEGMENTS || (n > 0 && !pts) || ((uintptr_t)pts & 15))
+    return set_error(PCS_ERR_BAD_ARG, "pcs_bounds_update: bad args (points must be 16-byte aligned)");
+  if (n == 0) return 0;
+  PCS_LAUNCH(bounds_update_kernel, grid_for(n, 256, 8), 256, 0, as_stream(s), (const float4 *)pts, (long long)n,
+             seg_div < 1 ? 1 : seg_div, n_seg, bounds);
+  return 0;
+}
+
+int pcs_grid_params(pcs_stream_t s, const uint32_t *bounds, int n_seg, const float *vs, float *seg_lo,
+                    int64_t *seg_dims) {
+  if (!bounds || !vs || !seg_lo || !seg_dims || n_seg < 1 || n_seg > PCS_MAX_SEGMENTS)
+    return set_error(PCS_ERR_BAD_ARG, "pcs_grid_params: bad args");
+  PCS_LAUNCH(grid_params_kernel, 1, 256, 0, as_stream(s), bounds, n_seg, vs[0], vs[1], vs[2], vs[3], seg_lo,
+             (long long *)seg_dims);
+  return 0;
+}
+
+int pcs_voxel_keys(pcs_stream_t s, const float *pts, int64_t n, int seg_div, int n_seg, const float *seg_lo,
+                   const int64_t *seg_dims, const float *vs, int64_t *coords, int64_t *keys) {
+  if (n_seg < 1 || n_seg > PCS_MAX_SEGMENTS || ((uintptr_t)pts & 15))
+    return set_error(PCS_ERR_BAD_ARG, "pcs_voxel_keys: bad args");
+  if (n == 0) return 0;
+  SegGeom g = make_geom(seg_lo, seg_dims, vs, seg_div, n_seg);
+  PCS_LAUNCH(voxel_keys_kernel, (unsigned)((n + 255) / 256), 256, 0, as_stream(s), (const float4 *)pts,
+             (long long)n, g, (long long *)coords, (long long *)keys);
+  return 0;
+}
+
+int pcs_hash_build(pcs_stream_t s, const float *pts, int64_t n, int seg_div, int n_seg, const float *seg_lo,
+                   const int64_t *seg_dims, const float *vs, pcs_slot_t *table, int64_t H, float *sorted_pts,
+                   int32_t *sorted_idx, int32_t *counters) {
+  if (!table || !counters || H < 2 || (H & (H - 1)) || n_seg < 1 || n_seg > PCS_MAX_SEGMENTS || n < 0 ||
+      n >= (1LL << 31) || ((uintptr_t)pts & 15) || ((uintptr_t)sorted_pts & 15) || ((uintptr_t)table & 15))
+    return set_error(PCS_ERR_BAD_ARG, "pcs_hash_build: bad args (H must be a power of two, buffers 16-byte aligned)");
+  cudaStream_t st = as_stream(s);
+  SegGeom g = make_geom(seg_lo, seg_dims, vs, seg_div, n_seg);
+  PCS_LAUNCH(table_clear_kernel, grid_for(H, 256, 8), 256, 0, st, (int4 *)table, (long long)H, counters);
+  if (n == 0) return 0;
+  PCS_LAUNCH(hash_count_kernel, grid_for(n, 256, 8), 256, 0, st, (const float4 *)pts, (long long)n, g, table,
+             (long long)(H - 1), counters);
+  PCS_LAUNCH(assign_ranges_kernel, (unsigned)((H + 1023) / 1024), 256, 0, st, table, (long long)H, counters);
+  PCS_LAUNCH(hash_scatter_kernel, grid_for(n, 256, 8), 256, 0, st, (const float4 *)pts, (long long)n, g, table,
+             (long long)(H - 1), (float4 *)sorted_pts, sorted_idx);
+  PCS_LAUNCH(rewind_ranges_kernel, (unsigned)((H + 255) / 256), 256, 0, st, table, (long long)H);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,280 @@
+"""Host-side wrappers of the C ABI (include/pcseq_b200.h) on torch CUDA tensors.
+
+torch is used for device memory and the current stream only; every computation on the path happens
+in libpcseq_b200.so.  All functions raise on CPU tensors -- there is no fallback.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+PCS_MAX_K = 32
+PCS_MAX_SEGMENTS = 64
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _f4(vals):
+    return (ctypes.c_float * 4)(*[float(v) for v in vals])
+
+
+def _i4(vals):
+    return (ctypes.c_int * 4)(*[int(v) for v in vals])
+
+
+def _as_points(t, name="points"):
+    """float32 [N,4] contiguous CUDA rows; [N,3] inputs (batch,x,y) get a zero 4th coordinate."""
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.PcsError(f"{name} must be a CUDA tensor (no CPU path exists)")
+    if t.dim() != 2 or t.shape[1] not in (3, 4):
+        raise _lib.PcsError(f"{name} must have shape [N,4] (or [N,3]), got {tuple(t.shape)}")
+    t = t.float()
+    if t.shape[1] == 3:
+        t = torch.cat([t, t.new_zeros(t.shape[0], 1)], 1)
+    t = t.contiguous()
+    if t.data_ptr() % 16:
+        t = t.clone()
+    return t
+
+
+def next_pow2(x):
+    return 1 << max(1, int(x - 1).bit_length())
+
+
+def radius_voxel_size(radius):
+    """[1 - 1e-3, r, r, r] in fp32 (graph_utils.py:170)."""
+    r = float(np.float32(radius))
+    return [float(np.float32(1 - 1e-3)), r, r, r]
+
+
+class CellGrid:
+    """Voxel hash of a reference point set: unique-cell open-addressing table + cell-sorted points.
+
+    Replaces the (keys, values, reverse_indices) multimap the reference allocates per RadiusGraph call
+    (graph_utils.py:179-192).  `bounds_sets` are the point sets whose joint min/max define the grid
+    origin (the reference uses ref U query, graph_utils.py:171-173).
+    """
+
+    def __init__(self, ref, voxel_size, bounds_sets=None, seg_div=1, n_seg=1, table_size=None):
+        L = _lib.lib()
+        self.ref = _as_points(ref, "ref")
+        dev = self.ref.device
+        self.n = self.ref.shape[0]
+        self.vs = [float(v) for v in voxel_size]
+        self.seg_div, self.n_seg = int(seg_div), int(n_seg)
+        if not (1 <= self.n_seg <= PCS_MAX_SEGMENTS):
+            raise _lib.PcsError(f"n_seg must be in [1, {PCS_MAX_SEGMENTS}]")
+        with torch.cuda.device(dev):
+            s = _stream()
+            self.bounds = torch.empty(self.n_seg * 8, dtype=torch.int32, device=dev)
+            _lib.check(L.pcs_bounds_init(s, _ptr(self.bounds), self.n_seg), "pcs_bounds_init")
+            sets = [self.ref] if bounds_sets is None else [_as_points(b, "bounds set") for b in bounds_sets]
+            seen = set()
+            for b in sets:
+                if b.data_ptr() in seen or b.shape[0] == 0:
+                    continue
+                seen.add(b.data_ptr())
+                _lib.check(L.pcs_bounds_update(s, _ptr(b), b.shape[0], self.seg_div, self.n_seg, _ptr(self.bounds)),
+                           "pcs_bounds_update")
+            self.seg_lo = torch.empty(self.n_seg, 4, dtype=torch.float32, device=dev)
+            self.seg_dims = torch.empty(self.n_seg, 4, dtype=torch.int64, device=dev)
+            _lib.check(L.pcs_grid_params(s, _ptr(self.bounds), self.n_seg, _f4(self.vs), _ptr(self.seg_lo),
+                                         _ptr(self.seg_dims)), "pcs_grid_params")
+            self.H = int(table_size) if table_size else next_pow2(max(2 * self.n, 1024))
+            self.table = torch.empty(self.H, 4, dtype=torch.int32, device=dev)  # pcs_slot_t[H]
+            self.sorted_pts = torch.empty(max(self.n, 1), 4, dtype=torch.float32, device=dev)
+            self.sorted_idx = torch.empty(max(self.n, 1), dtype=torch.int32, device=dev)
+            self.counters = torch.empty(4, dtype=torch.int32, device=dev)
+            _lib.check(L.pcs_hash_build(s, _ptr(self.ref), self.n, self.seg_div, self.n_seg, _ptr(self.seg_lo),
+                                        _ptr(self.seg_dims), _f4(self.vs), _ptr(self.table), self.H,
+                                        _ptr(self.sorted_pts), _ptr(self.sorted_idx), _ptr(self.counters)),
+                       "pcs_hash_build")
+
+    def check(self):
+        """Synchronising check of the device-side error flag (table full / key overflow)."""
+        c = self.counters.tolist()
+        if c[2] != 0:
+            raise _lib.PcsError(f"voxel hash build failed on device (code {c[2]})")
+        return c[0]  # number of occupied cells
+
+    def voxel_keys(self, pts):
+        """Reference-exact voxel coordinates int64[N,4] and linear keys int64[N] (graph_utils.py:174-175)."""
+        pts = _as_points(pts)
+        coords = torch.empty(pts.shape[0], 4, dtype=torch.int64, device=pts.device)
+        keys = torch.empty(pts.shape[0], dtype=torch.int64, device=pts.device)
+        with torch.cuda.device(pts.device):
+            _lib.check(_lib.lib().pcs_voxel_keys(_stream(), _ptr(pts), pts.shape[0], self.seg_div, self.n_seg,
+                                                 _ptr(self.seg_lo), _ptr(self.seg_dims), _f4(self.vs), _ptr(coords),
+                                                 _ptr(keys)), "pcs_voxel_keys")
+        return coords, keys
+
+    def search(self, query, K, radius, qmin=(0, -1, -1, -1), qmax=(0, 1, 1, 1), order=None, want_d2=False,
+               uf_parent=None, want_lists=True):
+        """K nearest reference points within `radius` of every query (padded lists).
+
+        radius: python float or float32 tensor [M].  Returns (nbr_idx i32[M,K] | None, nbr_cnt i32[M],
+        nbr_d2 f32[M,K] | None).
+        """
+        if not (1 <= K <= PCS_MAX_K):
+            raise _lib.PcsError(f"K must be in [1, {PCS_MAX_K}] (got {K})")
+        query = _as_points(query, "query")
+        m = query.shape[0]
+        dev = query.device
+        nbr_idx = torch.empty(m, K, dtype=torch.int32, device=dev) if want_lists else None
+        nbr_d2 = torch.empty(m, K, dtype=torch.float32, device=dev) if (want_d2 and want_lists) else None
+        nbr_cnt = torch.empty(m, dtype=torch.int32, device=dev)
+        rad_t, rad_s = None, 0.0
+        if isinstance(radius, torch.Tensor):
+            rad_t = radius.float().contiguous()
+        else:
+            rad_s = float(np.float32(radius))
+        if order is not None:
+            order = order.int().contiguous()
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().pcs_radius_search(
+                _stream(), _ptr(self.table), self.H, _ptr(self.sorted_pts), _ptr(self.sorted_idx), self.seg_div,
+                self.n_seg, _ptr(self.seg_lo), _ptr(self.seg_dims), _f4(self.vs), _ptr(query), m, _ptr(order),
+                _i4(qmin), _i4(qmax), _ptr(rad_t), rad_s, int(K), _ptr(nbr_idx), _ptr(nbr_d2), _ptr(nbr_cnt),
+                _ptr(uf_parent)), "pcs_radius_search")
+        return nbr_idx, nbr_cnt, nbr_d2
+
+
+def exclusive_scan(counts):
+    """int32[n] -> int64[n+1] exclusive prefix sums with the total in the last entry (no host sync)."""
+    counts = counts.int().contiguous()
+    n = counts.shape[0]
+    L = _lib.lib()
+    out = torch.empty(n + 1, dtype=torch.int64, device=counts.device)
+    tb = int(L.pcs_exclusive_scan_tmp_bytes(n))
+    tmp = torch.empty(tb, dtype=torch.uint8, device=counts.device)
+    with torch.cuda.device(counts.device):
+        _lib.check(L.pcs_exclusive_scan(_stream(), _ptr(counts), n, _ptr(out), _ptr(tmp), tb), "pcs_exclusive_scan")
+    return out
+
+
+def lists_to_edges(nbr_idx, nbr_cnt, nbr_d2=None):
+    """Padded lists -> (edges int64[E,2] rows (ref, query) by ascending query, dists | None).  One host sync (E)."""
+    m, K = nbr_idx.shape
+    offsets = exclusive_scan(nbr_cnt)
+    E = int(offsets[-1].item())
+    edges = torch.empty(E, 2, dtype=torch.int64, device=nbr_idx.device)
+    dists = torch.empty(E, dtype=torch.float32, device=nbr_idx.device) if nbr_d2 is not None else None
+    with torch.cuda.device(nbr_idx.device):
+        _lib.check(_lib.lib().pcs_lists_to_edges(_stream(), _ptr(nbr_idx), _ptr(nbr_d2), _ptr(nbr_cnt), _ptr(offsets),
+                                                 m, K, _ptr(edges), _ptr(dists)), "pcs_lists_to_edges")
+    return edges, dists
+
+
+def radius_graph(ref, query, radius, max_num_neighbors=32, sort_by_dist=True, qmin=(0, -1, -1, -1),
+                 qmax=(0, 1, 1, 1), return_dists=False):
+    """RadiusGraph.build_graph (graph_utils.py:149-209) on the new kernels -> (e_ref, e_query[, d2]).
+
+    The K kept neighbours are always the K nearest (ties by ascending reference index); with
+    sort_by_dist=False the reference keeps the first K in its race-dependent discovery order, of
+    which "the K nearest" is one legal outcome.
+    """
+    ref = _as_points(ref, "ref")
+    same = query is ref
+    query = ref if same else _as_points(query, "query")
+    if ref.shape[0] == 0 or query.shape[0] == 0:
+        z = torch.zeros(0, dtype=torch.int64, device=ref.device)
+        return (z, z.clone(), torch.zeros(0, device=ref.device)) if return_dists else (z, z.clone())
+    rmax = float(radius.max().item()) if isinstance(radius, torch.Tensor) else float(np.float32(radius))
+    grid = CellGrid(ref, radius_voxel_size(rmax), bounds_sets=[ref, query])
+    K = int(max_num_neighbors)
+    if K < 1 or K > PCS_MAX_K:
+        raise _lib.PcsError(f"max_num_neighbors must be in [1, {PCS_MAX_K}] on this path (got {K})")
+    order = grid.sorted_idx[:grid.n] if same else None  # cell-coherent query order for self graphs
+    nbr_idx, nbr_cnt, nbr_d2 = grid.search(query, K, radius, qmin, qmax, order=order, want_d2=return_dists)
+    edges, dists = lists_to_edges(nbr_idx, nbr_cnt, nbr_d2)
+    grid.check()
+    if return_dists:
+        return edges[:, 0], edges[:, 1], dists
+    return edges[:, 0], edges[:, 1]
+
+
+def connected_components(edges, num_nodes, seg_of=None, n_seg=1):
+    """graph_utils.connected_components (graph_utils.py:40-53) on the device.
+
+    edges int64[2,E] (or a pair of int64[E]).  Returns (n_comp int64[n_seg] tensor, labels int64[N]).
+    """
+    e0, e1 = edges[0].long().contiguous(), edges[1].long().contiguous()
+    dev = e0.device
+    L = _lib.lib()
+    parent = torch.empty(num_nodes, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        s = _stream()
+        _lib.check(L.pcs_uf_init(s, _ptr(parent), num_nodes), "pcs_uf_init")
+        _lib.check(L.pcs_uf_union_edges(s, _ptr(parent), _ptr(e0), _ptr(e1), e0.shape[0]), "pcs_uf_union_edges")
+    return uf_labels(parent, seg_of, n_seg)
+
+
+def uf_new(n, device):
+    parent = torch.empty(n, dtype=torch.int32, device=device)
+    with torch.cuda.device(device):
+        _lib.check(_lib.lib().pcs_uf_init(_stream(), _ptr(parent), n), "pcs_uf_init")
+    return parent
+
+
+def uf_labels(parent, seg_of=None, n_seg=1):
+    n = parent.shape[0]
+    dev = parent.device
+    L = _lib.lib()
+    labels = torch.empty(n, dtype=torch.int64, device=dev)
+    n_comp = torch.zeros(n_seg, dtype=torch.int64, device=dev)
+    tb = int(L.pcs_uf_labels_tmp_bytes(n, n_seg))
+    tmp = torch.empty(max(tb, 8), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(L.pcs_uf_labels(_stream(), _ptr(parent), n, _ptr(seg_of), n_seg, _ptr(labels), _ptr(n_comp),
+                                   _ptr(tmp), tb), "pcs_uf_labels")
+    return n_comp, labels
+
+
+def point_segments(pts, seg_div, n_seg):
+    pts = _as_points(pts)
+    out = torch.empty(pts.shape[0], dtype=torch.int32, device=pts.device)
+    with torch.cuda.device(pts.device):
+        _lib.check(_lib.lib().pcs_point_segments(_stream(), _ptr(pts), pts.shape[0], seg_div, n_seg, _ptr(out)),
+                   "pcs_point_segments")
+    return out
+
+
+def cluster_labels(fxyz, radius, max_num_neighbors=32, chunk=10, num_frames=None, grid=None):
+    """Fused cluster proposal for one radius: intra-frame K-nearest radius graph per `chunk`-frame
+    segment + connected components, without materialising edges.
+
+    Equals ClusterProposal.propose_cluster's inner loop (cluster_proposal.py:63-81): labels are numbered
+    per chunk by ascending smallest member index with a running offset.  Returns (labels int64[N],
+    n_comp int64[n_seg]).
+    """
+    fxyz = _as_points(fxyz, "point_fxyz")
+    n = fxyz.shape[0]
+    if num_frames is None:
+        num_frames = int(fxyz[:, 0].max().item()) + 1
+    n_seg = max(1, (num_frames + chunk - 1) // chunk)
+    if n_seg > PCS_MAX_SEGMENTS:
+        raise _lib.PcsError(f"{n_seg} chunks exceed PCS_MAX_SEGMENTS={PCS_MAX_SEGMENTS}")
+    if grid is None:
+        grid = CellGrid(fxyz, radius_voxel_size(radius), seg_div=chunk, n_seg=n_seg)
+    parent = uf_new(n, fxyz.device)
+    grid.search(fxyz, int(max_num_neighbors), radius, order=grid.sorted_idx[:n], uf_parent=parent,
+                want_lists=False)
+    seg_of = point_segments(fxyz, chunk, n_seg)
+    n_comp, labels = uf_labels(parent, seg_of, n_seg)
+    return labels, n_comp
+
+
+def launch_count():
+    return int(_lib.lib().pcs_launch_count())
+
+
+def reset_launch_count():
+    _lib.lib().pcs_reset_launch_count()
