@@ -125,7 +125,15 @@ __global__ void __launch_bounds__(kLabBlock) uf_flatten_count_kernel(int *__rest
   __syncthreads();
   long long i = (long long)blockIdx.x * kLabBlock + threadIdx.x;
   if (i < n) {
-    int r = uf_find(parent, (int)i);
+    // read-only walk: the only writer of parent[i] in this pass is thread i, so a stale path-halving
+    // store can never overwrite the root written below
+    volatile int *p = parent;
+    int r = (int)i;
+    while (true) {
+      int pr = p[r];
+      if (pr == r) break;
+      r = pr;
+    }
     parent[i] = r;
     if (r == (int)i) atomicAdd(&hist[seg_of ? seg_of[i] : 0], 1);
   }
