@@ -81,6 +81,8 @@ int pcs_hash_build(pcs_stream_t s, const float *pts, int64_t n, int seg_div, int
  * (torch_hash_kernel.cu:224-409, 487-561) in ONE pass: for every query the cells
  * [c + qmin, c + qmax] are looked up, candidates are filtered by the fp32 4-D distance test
  * d2 <= r*r (same FMA order as the reference) and the K nearest are kept.
+ *   queries    float4[m]; NULL = self-query mode: the grid's own points are the queries (m == n), read
+ *              in cell order straight from sorted_pts / sorted_idx (outputs indexed by original row)
  *   order      optional int32[m]: the i-th work item processes query order[i] (cell-coherent order)
  *   radius     optional float[m] per-query radius; NULL -> radius_scalar
  *   K          1..32 neighbours kept (the K smallest (d2, ref index) pairs; ties by ascending index)
@@ -121,6 +123,37 @@ int pcs_uf_labels(pcs_stream_t s, int32_t *parent, int64_t n, const int32_t *seg
 int64_t pcs_uf_labels_tmp_bytes(int64_t n, int n_seg);
 /* int32 segment id per point from the frame column (seg = min(int(frame)/seg_div, n_seg-1)). */
 int pcs_point_segments(pcs_stream_t s, const float *pts, int64_t n, int seg_div, int n_seg, int32_t *seg_of);
+
+/* ---- voxelization ----------------------------------------------------------------------------
+ * Replaces GridSampling3D.forward (pcdet/models/model_utils/grid_sampling.py:22-46):
+ * torch_cluster.grid_cluster (truncation-based cell key, frame digit fastest) -> torch.unique(sorted,
+ * return_inverse) -> torch_scatter.scatter(mean); plus scatter(arange, inv, 'max') of
+ * simple_reg.py:122-124 and robust_median of registration_utils.py:60-81.
+ *   bounds   uint32[8] from pcs_bounds_* with n_seg = 1
+ *   size     (host) float[4] = [1, gx, gy, gz]
+ *   start    float[4] (device), strides int64[5] (device; [4] = cells of the bounding grid)
+ *   table    16-byte slots [H] (H power of two, cleared by the call), pt_slot int32[n]
+ *   sums     optional double[H][4] (per-slot fp64 sums), maxidx optional int32[H]
+ *   ukeys / uslots  int64[n] / int32[n]: unique keys and their slots in claim order;
+ *   counters int32[4]: [0] = V (number of voxels), [2] = error flag
+ * pcs_sort_pairs sorts the V unique (key, slot) pairs by key (radix sort);
+ * pcs_voxelize_finish numbers voxels by ascending key and writes inv int64[n], sampled float4[V]
+ * (mean of all four columns), maxidx_out int64[V], counts_out int32[V] (any may be NULL). */
+int pcs_voxelize_params(pcs_stream_t s, const uint32_t *bounds, const float *size, int ignore_dim0, float *start,
+                        int64_t *strides);
+int pcs_voxelize_insert(pcs_stream_t s, const float *pts, int64_t n, const float *start, const int64_t *strides,
+                        const float *size, int ignore_dim0, void *table, int64_t H, int32_t *pt_slot, double *sums,
+                        int32_t *maxidx, int64_t *ukeys, int32_t *uslots, int32_t *counters);
+int64_t pcs_sort_pairs_tmp_bytes(int64_t n);
+int pcs_sort_pairs(pcs_stream_t s, const int64_t *keys_in, int64_t *keys_out, const int32_t *vals_in,
+                   int32_t *vals_out, int64_t n, void *tmp, int64_t tmp_bytes);
+int pcs_voxelize_finish(pcs_stream_t s, void *table, int64_t H, const int32_t *uslots_sorted, int64_t V,
+                        const int32_t *pt_slot, int64_t n, const double *sums, const int32_t *maxidx, int64_t *inv,
+                        float *sampled, int64_t *maxidx_out, int32_t *counts_out);
+/* Upper median per group (rank deg/2 of the sorted values; empty groups -> -1e10).  offsets int64[V+1]
+ * = exclusive scan of the group sizes, cursor int32[V] zero-filled scratch, rows int32[n] scratch. */
+int pcs_group_median(pcs_stream_t s, const int64_t *values, const int64_t *inv, int64_t n, const int64_t *offsets,
+                     int64_t V, int32_t *cursor_zeroed, int32_t *rows, int64_t *out);
 
 #ifdef __cplusplus
 }

@@ -2,14 +2,19 @@
 //
 // Replaces count_radius_graph_degree_kernel + radius_graph_kernel
 // (pcdet/ops/torch_hash/src/torch_hash_kernel.cu:224-409).  One warp owns one query:
-//   1. the lanes look up the (up to 27) neighbour cells in parallel -- one 128-bit slot load each;
-//   2. the cells' row ranges are concatenated into one virtual candidate range, which the warp
-//      sweeps 32 candidates at a time with coalesced float4 loads of the cell-sorted points;
-//   3. candidates that pass the reference's fp32 test d2 <= r*r are ballot-compacted and inserted
-//      into a sorted K-list held one entry per lane (64-bit key = d2 bits : row index, so ties are
-//      broken by ascending reference index -- the canonical order of SURVEY.md A.4);
-//   4. the list is written as one coalesced row, or -- fused connected components -- every
-//      (query, neighbour) pair is united in the union-find forest and nothing else is written.
+//   1. every lane derives one neighbour cell (up to 27), a conservative lower bound `dmin2` of the
+//      squared distance from the query to anything stored in that cell, and -- unless the cell lies
+//      beyond the radius -- looks the cell up with one 128-bit slot load;
+//   2. cells are visited in ascending dmin2 (warp redux-min selection); the sweep stops as soon as
+//      dmin2 exceeds min(r^2, current K-th best distance): nothing in the remaining cells can enter
+//      the list, so the result is exactly the K nearest of the reference's 27-cell candidate set;
+//   3. a cell's rows are swept 32 at a time with coalesced float4 loads of the cell-sorted points;
+//      the reference's fp32 test d2 <= r*r (same FMA order) and a float compare against the K-th best
+//      gate a ballot-compacted insertion into a sorted K-list held one entry per lane (64-bit key =
+//      d2 bits : row index, so ties are broken by ascending reference index -- SURVEY.md A.4);
+//   4. the list is written as one coalesced row, or -- fused connected components -- the roots of
+//      the query and all its neighbours are hooked under their minimum in the union-find forest and
+//      no edge is ever written.
 #include "common.cuh"
 
 namespace pcs {
@@ -21,6 +26,17 @@ struct QueryRange {
 };
 
 constexpr int kWarpsPerBlock = 8;
+constexpr unsigned int kFull = 0xffffffffu;
+
+// lower bound (in metres) of |p_i - q_i| for points stored `o` cells away along one axis;
+// u = (q - lo)/vs as computed for the key, f = u - rint(u).  The margin covers the fp32 rounding of u
+// for both the query and the stored point (2 * |u| * 2^-23 cells) with a 16x safety factor.
+__device__ __forceinline__ float axis_gap(int o, float f, float u, float vs) {
+  if (o == 0) return 0.f;
+  float g = (o > 0) ? ((float)o - 0.5f - f) : ((float)(-o) - 0.5f + f);
+  g -= 4e-6f * (fabsf(u) + 1.0f);
+  return g > 0.f ? g * vs : 0.f;
+}
 
 template <bool kFusedUF>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
@@ -31,8 +47,6 @@ radius_search_kernel(const pcs_slot_t *__restrict__ table, long long mask, const
                      int *__restrict__ nbr_cnt, int *__restrict__ uf_parent) {
   __shared__ float4 s_lo[PCS_MAX_SEGMENTS];
   __shared__ long long s_dims[PCS_MAX_SEGMENTS * 4];
-  __shared__ int s_pref[kWarpsPerBlock][33];
-  __shared__ int s_start[kWarpsPerBlock][32];
   load_geom(g, s_lo, s_dims);
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -40,24 +54,31 @@ radius_search_kernel(const pcs_slot_t *__restrict__ table, long long mask, const
   const unsigned long long kInf = ~0ull;
 
   for (long long w = (long long)blockIdx.x * kWarpsPerBlock + warp; w < m; w += nwarps) {
-    const long long q = order ? (long long)order[w] : w;
-    const float4 qp = queries[q];
+    // self-query mode (queries == NULL): the w-th row of the cell-sorted array queries its own grid
+    const long long q = queries ? (order ? (long long)order[w] : w) : (long long)sorted_idx[w];
+    const float4 qp = queries ? queries[q] : sorted_pts[w];
     const float r = radius ? radius[q] : radius_scalar;
     const float r2 = __fmul_rn(r, r);
     const int seg = point_segment(qp.x, g.seg_div, g.n_seg);
     const float4 lo = s_lo[seg];
     const long long *dims = s_dims + seg * 4;
-    const long long qc0 = voxel_coord(qp.x, lo.x, g.vs[0]);
-    const long long qc1 = voxel_coord(qp.y, lo.y, g.vs[1]);
-    const long long qc2 = voxel_coord(qp.z, lo.z, g.vs[2]);
-    const long long qc3 = voxel_coord(qp.w, lo.w, g.vs[3]);
+    // voxel coordinates exactly as voxel_coord() computes them, keeping u for the pruning bound
+    const float u0 = __fdiv_rn(__fsub_rn(qp.x, lo.x), g.vs[0]);
+    const float u1 = __fdiv_rn(__fsub_rn(qp.y, lo.y), g.vs[1]);
+    const float u2 = __fdiv_rn(__fsub_rn(qp.z, lo.z), g.vs[2]);
+    const float u3 = __fdiv_rn(__fsub_rn(qp.w, lo.w), g.vs[3]);
+    const float n0 = rintf(u0), n1 = rintf(u1), n2 = rintf(u2), n3 = rintf(u3);
+    const long long qc0 = (long long)n0 + 1, qc1 = (long long)n1 + 1, qc2 = (long long)n2 + 1,
+                    qc3 = (long long)n3 + 1;
 
     unsigned long long best = kInf;  // lane j holds the j-th smallest (d2, index) key
-    int accepted = 0;
+    float worst_d2 = __int_as_float(0x7f800000);  // d2 of list entry K-1 (+inf while the list is not full)
+    int fill = 0;                                 // number of valid list entries (<= K)
 
     for (int cb = 0; cb < qr.nc; cb += 32) {
-      // ---- 1. parallel cell lookups ----------------------------------------------------------
+      // ---- 1. per-lane cell: offset, pruning bound, lookup -----------------------------------
       int start = 0, count = 0;
+      unsigned int sel = 0xffffffffu;  // selection key: dmin2 bits (low 5 cleared) | lane ; ~0 = nothing to visit
       const int cell = cb + lane;
       if (cell < qr.nc) {
         int t = cell;
@@ -68,73 +89,92 @@ radius_search_kernel(const pcs_slot_t *__restrict__ table, long long mask, const
         const int o2 = t % qr.range[2] + qr.qmin[2];
         t /= qr.range[2];
         const int o3 = t % qr.range[3] + qr.qmin[3];
-        const long long key =
-            map2key4(qc0 + o0, qc1 + o1, qc2 + o2, qc3 + o3, dims) | ((long long)seg << PCS_SEG_SHIFT);
-        long long slot = hash_key(key) & mask;
-        for (long long probes = 0; probes <= mask; ++probes) {
-          const int4 v = __ldg(reinterpret_cast<const int4 *>(table + slot));
-          const long long k = ((long long)v.y << 32) | (unsigned int)v.x;
-          if (k == key) {
-            start = v.z;
-            count = v.w;
-            break;
+        const long long c0 = qc0 + o0, c1 = qc1 + o1, c2 = qc2 + o2, c3 = qc3 + o3;
+        float dmin2 = 0.f;
+        // if map2key clamps a digit the cell aliases another one (reference quirk): no geometric bound then
+        const bool clamped = c0 < 0 || c0 > dims[0] || c1 < 0 || c1 > dims[1] || c2 < 0 || c2 > dims[2] ||
+                             c3 < 0 || c3 > dims[3];
+        if (!clamped) {
+          const float g1 = axis_gap(o1, u1 - n1, u1, g.vs[1]);
+          const float g2 = axis_gap(o2, u2 - n2, u2, g.vs[2]);
+          const float g3 = axis_gap(o3, u3 - n3, u3, g.vs[3]);
+          dmin2 = g1 * g1 + g2 * g2 + g3 * g3;  // dimension 0 (frame) is left out: bound stays conservative
+          dmin2 *= 0.99999f;
+        }
+        if (dmin2 <= r2) {
+          const long long key = map2key4(c0, c1, c2, c3, dims) | ((long long)seg << PCS_SEG_SHIFT);
+          long long slot = hash_key(key) & mask;
+          for (long long probes = 0; probes <= mask; ++probes) {
+            const int4 v = __ldg(reinterpret_cast<const int4 *>(table + slot));
+            const long long k = ((long long)v.y << 32) | (unsigned int)v.x;
+            if (k == key) {
+              start = v.z;
+              count = v.w;
+              break;
+            }
+            if (k == PCS_EMPTY_KEY) break;
+            slot = (slot + 1) & mask;
           }
-          if (k == PCS_EMPTY_KEY) break;
-          slot = (slot + 1) & mask;
+          if (count > 0) sel = (__float_as_uint(dmin2) & ~31u) | (unsigned int)lane;
         }
       }
-      const int incl = warp_incl_scan(count, lane);
-      const int total = __shfl_sync(0xffffffffu, incl, 31);
-      if (total == 0) continue;
-      __syncwarp();
-      s_pref[warp][lane] = incl - count;
-      s_start[warp][lane] = start;
-      if (lane == 31) s_pref[warp][32] = total;
-      __syncwarp();
 
-      // ---- 2./3. sweep the concatenated candidate range --------------------------------------
-      int c = 0;
-      const int total_round = (total + 31) & ~31;
-      for (int j = lane; j < total_round; j += 32) {
-        unsigned long long key64 = kInf;
-        bool within = false;
-        if (j < total) {
-          while (j >= s_pref[warp][c + 1]) ++c;
-          const int src = s_start[warp][c] + (j - s_pref[warp][c]);
-          const float4 p = __ldg(sorted_pts + src);
-          const float d2 = dist2_ref(p, qp);
-          within = d2 <= r2;
-          if (within)
-            key64 = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned int)__ldg(sorted_idx + src);
-        }
-        const unsigned int wmask = __ballot_sync(0xffffffffu, within);
-        if (wmask == 0) continue;
-        accepted += __popc(wmask);
-        unsigned long long worst = __shfl_sync(0xffffffffu, best, K - 1);
-        unsigned int cand = __ballot_sync(0xffffffffu, within && key64 < worst);
-        while (cand) {
-          const int srcl = __ffs(cand) - 1;
-          cand &= cand - 1;
-          const unsigned long long ck = __shfl_sync(0xffffffffu, key64, srcl);
-          if (ck < worst) {  // warp-uniform
-            const unsigned long long up = __shfl_up_sync(0xffffffffu, best, 1);
-            const bool gt = best > ck;
-            const bool gt_prev = (lane > 0) && (up > ck);
-            if (gt) best = gt_prev ? up : ck;
-            worst = __shfl_sync(0xffffffffu, best, K - 1);
+      // ---- 2. visit cells in ascending dmin2 ---------------------------------------------------
+      while (true) {
+        const unsigned int pick = __reduce_min_sync(kFull, sel);
+        if (pick == 0xffffffffu) break;
+        const float pick_d = __uint_as_float(pick & ~31u);
+        if (pick_d > fminf(r2, worst_d2)) break;  // every remaining cell is at least this far
+        const int src_lane = pick & 31;
+        if (lane == src_lane) sel = 0xffffffffu;
+        const int cstart = __shfl_sync(kFull, start, src_lane);
+        const int ccount = __shfl_sync(kFull, count, src_lane);
+
+        // ---- 3. sweep the cell, 32 rows per step ----------------------------------------------
+        for (int j0 = 0; j0 < ccount; j0 += 32) {
+          const int j = j0 + lane;
+          float d2 = __int_as_float(0x7f800000);
+          if (j < ccount) d2 = dist2_ref(__ldg(sorted_pts + cstart + j), qp);
+          // reference acceptance d2 <= r*r, and it must not be worse than the current K-th best
+          const bool pass = (d2 <= r2) && (d2 <= worst_d2);
+          unsigned int cand = __ballot_sync(kFull, pass);
+          if (cand == 0) continue;
+          unsigned long long key64 = kInf;
+          if (pass)
+            key64 = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned int)__ldg(sorted_idx + cstart + j);
+          unsigned long long worst = __shfl_sync(kFull, best, K - 1);
+          while (cand) {
+            const int srcl = __ffs(cand) - 1;
+            cand &= cand - 1;
+            const unsigned long long ck = __shfl_sync(kFull, key64, srcl);
+            if (ck < worst) {  // warp-uniform
+              const unsigned long long up = __shfl_up_sync(kFull, best, 1);
+              const bool gt = best > ck;
+              const bool gt_prev = (lane > 0) && (up > ck);
+              if (gt) best = gt_prev ? up : ck;
+              worst = __shfl_sync(kFull, best, K - 1);
+              if (fill < K) ++fill;
+            }
           }
+          if (fill == K) worst_d2 = __uint_as_float((unsigned int)(worst >> 32));
         }
       }
     }
 
     // ---- 4. emit ---------------------------------------------------------------------------------
-    const int cnt = accepted < K ? accepted : K;
+    const int cnt = fill;
     const int idx = (int)(unsigned int)(best & 0xffffffffu);
     if (nbr_idx && lane < K) nbr_idx[q * K + lane] = lane < cnt ? idx : -1;
     if (nbr_d2 && lane < K) nbr_d2[q * K + lane] = lane < cnt ? __uint_as_float((unsigned int)(best >> 32)) : 0.f;
     if (nbr_cnt && lane == 0) nbr_cnt[q] = cnt;
     if (kFusedUF) {
-      if (lane < cnt && idx != (int)q) uf_unite(uf_parent, (int)q, idx);
+      // hook the roots of the query and of all its neighbours under the smallest of them
+      const int node = lane < cnt ? idx : (int)q;
+      const int root = uf_find(uf_parent, node);
+      const int rmin = (int)__reduce_min_sync(kFull, (unsigned int)root);
+      const unsigned int peers = __match_any_sync(kFull, root);
+      if (root != rmin && lane == __ffs(peers) - 1) uf_unite(uf_parent, root, rmin);
+      if (cnt == 32 && lane == 0) uf_unite(uf_parent, (int)q, rmin);
     }
   }
 }
@@ -187,7 +227,7 @@ int pcs_radius_search(pcs_stream_t s, const pcs_slot_t *table, int64_t H, const 
   }
   SegGeom g = make_geom(seg_lo, seg_dims, vs, seg_div, n_seg);
   long long blocks = (m + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  long long cap = 148LL * 8 * 4;  // persistent-ish: a few waves of 8 resident CTAs per SM
+  long long cap = 148LL * 8 * 4;  // a few waves of 8 resident CTAs per SM; warps stride over the queries
   int grid = (int)(blocks < cap ? blocks : cap);
   if (uf_parent) {
     PCS_LAUNCH(radius_search_kernel<true>, grid, kWarpsPerBlock * 32, 0, as_stream(s), table, (long long)(H - 1),

@@ -120,14 +120,18 @@ class CellGrid:
                uf_parent=None, want_lists=True):
         """K nearest reference points within `radius` of every query (padded lists).
 
+        query=None is the self-query mode: the grid's own points are the queries and are visited in
+        cell order straight from the cell-sorted array (outputs are still indexed by original row).
         radius: python float or float32 tensor [M].  Returns (nbr_idx i32[M,K] | None, nbr_cnt i32[M],
         nbr_d2 f32[M,K] | None).
         """
         if not (1 <= K <= PCS_MAX_K):
             raise _lib.PcsError(f"K must be in [1, {PCS_MAX_K}] (got {K})")
-        query = _as_points(query, "query")
-        m = query.shape[0]
-        dev = query.device
+        if query is None:
+            m, dev = self.n, self.ref.device
+        else:
+            query = _as_points(query, "query")
+            m, dev = query.shape[0], query.device
         nbr_idx = torch.empty(m, K, dtype=torch.int32, device=dev) if want_lists else None
         nbr_d2 = torch.empty(m, K, dtype=torch.float32, device=dev) if (want_d2 and want_lists) else None
         nbr_cnt = torch.empty(m, dtype=torch.int32, device=dev)
@@ -192,8 +196,7 @@ def radius_graph(ref, query, radius, max_num_neighbors=32, sort_by_dist=True, qm
     K = int(max_num_neighbors)
     if K < 1 or K > PCS_MAX_K:
         raise _lib.PcsError(f"max_num_neighbors must be in [1, {PCS_MAX_K}] on this path (got {K})")
-    order = grid.sorted_idx[:grid.n] if same else None  # cell-coherent query order for self graphs
-    nbr_idx, nbr_cnt, nbr_d2 = grid.search(query, K, radius, qmin, qmax, order=order, want_d2=return_dists)
+    nbr_idx, nbr_cnt, nbr_d2 = grid.search(None if same else query, K, radius, qmin, qmax, want_d2=return_dists)
     edges, dists = lists_to_edges(nbr_idx, nbr_cnt, nbr_d2)
     grid.check()
     if return_dists:
@@ -265,11 +268,91 @@ def cluster_labels(fxyz, radius, max_num_neighbors=32, chunk=10, num_frames=None
     if grid is None:
         grid = CellGrid(fxyz, radius_voxel_size(radius), seg_div=chunk, n_seg=n_seg)
     parent = uf_new(n, fxyz.device)
-    grid.search(fxyz, int(max_num_neighbors), radius, order=grid.sorted_idx[:n], uf_parent=parent,
-                want_lists=False)
+    grid.search(None, int(max_num_neighbors), radius, uf_parent=parent, want_lists=False)
     seg_of = point_segments(fxyz, chunk, n_seg)
     n_comp, labels = uf_labels(parent, seg_of, n_seg)
     return labels, n_comp
+
+
+def voxelize(points, grid_size, ignore_dim0=False, want_mean=True, want_max=False, want_counts=False):
+    """GridSampling3D.forward on the device (grid_sampling.py:22-46).
+
+    points f32[N,4]; grid_size [gx,gy,gz] (the frame digit has size 1).  Voxels are numbered by ascending
+    cell key (torch.unique(sorted=True)).  Returns a dict with `inv` int64[N], `num` (python int, one host
+    sync) and optionally `sampled` f32[V,4] (mean of all columns), `maxidx` int64[V] (highest point index
+    per voxel: simple_reg.py:122-124), `counts` int32[V].  ignore_dim0 treats column 0 as zero
+    (preprocessor_utils.grid_sample :21-30).
+    """
+    pts = _as_points(points, "points")
+    n, dev = pts.shape[0], pts.device
+    L = _lib.lib()
+    size = [1.0] + [float(np.float32(g)) for g in grid_size]
+    out = {}
+    if n == 0:
+        out.update(inv=torch.zeros(0, dtype=torch.int64, device=dev), num=0)
+        return out
+    with torch.cuda.device(dev):
+        s = _stream()
+        bounds = torch.empty(8, dtype=torch.int32, device=dev)
+        _lib.check(L.pcs_bounds_init(s, _ptr(bounds), 1), "pcs_bounds_init")
+        _lib.check(L.pcs_bounds_update(s, _ptr(pts), n, 1, 1, _ptr(bounds)), "pcs_bounds_update")
+        start = torch.empty(4, dtype=torch.float32, device=dev)
+        strides = torch.empty(5, dtype=torch.int64, device=dev)
+        _lib.check(L.pcs_voxelize_params(s, _ptr(bounds), _f4(size), int(ignore_dim0), _ptr(start), _ptr(strides)),
+                   "pcs_voxelize_params")
+        H = next_pow2(max(2 * n, 1024))
+        table = torch.empty(H, 4, dtype=torch.int32, device=dev)
+        pt_slot = torch.empty(n, dtype=torch.int32, device=dev)
+        sums = torch.empty(H, 4, dtype=torch.float64, device=dev) if want_mean else None
+        maxidx = torch.empty(H, dtype=torch.int32, device=dev) if want_max else None
+        ukeys = torch.empty(n, dtype=torch.int64, device=dev)
+        uslots = torch.empty(n, dtype=torch.int32, device=dev)
+        counters = torch.empty(4, dtype=torch.int32, device=dev)
+        _lib.check(L.pcs_voxelize_insert(s, _ptr(pts), n, _ptr(start), _ptr(strides), _f4(size), int(ignore_dim0),
+                                         _ptr(table), H, _ptr(pt_slot), _ptr(sums), _ptr(maxidx), _ptr(ukeys),
+                                         _ptr(uslots), _ptr(counters)), "pcs_voxelize_insert")
+        c = counters.tolist()  # host sync: V is needed to size the outputs
+        if c[2] != 0:
+            raise _lib.PcsError(f"voxelize failed on device (code {c[2]})")
+        V = c[0]
+        tb = int(L.pcs_sort_pairs_tmp_bytes(V))
+        tmp = torch.empty(tb, dtype=torch.uint8, device=dev)
+        keys_sorted = torch.empty(V, dtype=torch.int64, device=dev)
+        slots_sorted = torch.empty(V, dtype=torch.int32, device=dev)
+        _lib.check(L.pcs_sort_pairs(s, _ptr(ukeys), _ptr(keys_sorted), _ptr(uslots), _ptr(slots_sorted), V, _ptr(tmp),
+                                    tb), "pcs_sort_pairs")
+        inv = torch.empty(n, dtype=torch.int64, device=dev)
+        sampled = torch.empty(V, 4, dtype=torch.float32, device=dev) if want_mean else None
+        maxidx_out = torch.empty(V, dtype=torch.int64, device=dev) if want_max else None
+        counts = torch.empty(V, dtype=torch.int32, device=dev) if want_counts else None
+        _lib.check(L.pcs_voxelize_finish(s, _ptr(table), H, _ptr(slots_sorted), V, _ptr(pt_slot), n, _ptr(sums),
+                                         _ptr(maxidx), _ptr(inv), _ptr(sampled), _ptr(maxidx_out), _ptr(counts)),
+                   "pcs_voxelize_finish")
+    out.update(inv=inv, num=V, keys=keys_sorted)
+    if want_mean:
+        out["sampled"] = sampled
+    if want_max:
+        out["maxidx"] = maxidx_out
+    if want_counts:
+        out["counts"] = counts
+    return out
+
+
+def group_median(values, inv, num_groups, counts=None):
+    """robust_median (registration_utils.py:60-81): upper median of int64 `values` per group `inv`."""
+    values = values.long().contiguous().reshape(-1)
+    inv = inv.long().contiguous()
+    n, dev = values.shape[0], values.device
+    if counts is None:
+        counts = torch.bincount(inv, minlength=num_groups).int()
+    offsets = exclusive_scan(counts)
+    cursor = torch.zeros(max(num_groups, 1), dtype=torch.int32, device=dev)
+    rows = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    out = torch.empty(num_groups, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().pcs_group_median(_stream(), _ptr(values), _ptr(inv), n, _ptr(offsets), num_groups,
+                                               _ptr(cursor), _ptr(rows), _ptr(out)), "pcs_group_median")
+    return out
 
 
 def launch_count():

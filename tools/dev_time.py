@@ -1,5 +1,7 @@
 """Developer timing of the individual kernels on a synthetic sequence (not the bench contract)."""
+import os
 import sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import time
 
 import torch
@@ -40,12 +42,12 @@ def main():
         grid = ops.CellGrid(f, vs, seg_div=10, n_seg=n_seg)
         cells = grid.check()
         parent = ops.uf_new(n, f.device)
-        ts = ev_time(lambda: grid.search(f, 32, r, order=grid.sorted_idx[:n], uf_parent=parent, want_lists=False), 3)
-        tl = ev_time(lambda: grid.search(f, 32, r, order=grid.sorted_idx[:n]), 3)
+        ts = ev_time(lambda: grid.search(None, 32, r, uf_parent=parent, want_lists=False), 3)
+        tl = ev_time(lambda: grid.search(None, 32, r), 3)
         tn = ev_time(lambda: grid.search(f, 32, r), 3)
         seg_of = ops.point_segments(f, 10, n_seg)
         tc = ev_time(lambda: ops.uf_labels(parent, seg_of, n_seg))
-        nb, cnt, _ = grid.search(f, 32, r, order=grid.sorted_idx[:n])
+        nb, cnt, _ = grid.search(None, 32, r)
         E = int(cnt.sum().item())
         print(f"r={r}: cells={cells} H={grid.H} build={tb[0]:.3f}ms  search+uf={ts[0]:.3f}ms  search(lists)={tl[0]:.3f}ms "
               f"search(unordered)={tn[0]:.3f}ms labels={tc[0]:.3f}ms  E={E} "
