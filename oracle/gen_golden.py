@@ -166,7 +166,29 @@ def main():
     gen_grid_sampling()
     gen_proposal()
     gen_registration()
+    gen_ground()
 
 
 if __name__ == "__main__":
     main()
+
+
+def gen_ground():
+    """ground_plane_removal (preprocessor_utils.py:352-419) with the north-star yaml's GroundPlaneRemover block."""
+    pu = R.load("pcdet.models.registration.preprocessors.preprocessor_utils")
+    from . import cpu_ops as ops
+    b, f, seg = _scene(6, 6, 32, 900)
+    pick = ops.subsample_pick(f.numpy())
+    f = f[torch.from_numpy(pick)]
+    seg = seg[torch.from_numpy(pick)]
+    cfg = R.edict(PILLAR_SIZE=[2, 2], LR=0.01, DECAY_STEPS=[1600], RIGID_WEIGHT=0.5, MAX_NUM_ITERS=10000,
+                  TRUNCATE_HEIGHT=[0.5], RANSAC=True, SIGMA2=0.0025, JointOpt=True, K=8)
+    torch.manual_seed(0)
+    height, horizon, err, pillar_height, pillar_min_z = pu.ground_plane_removal(f.clone(), cfg)
+    np.savez_compressed(os.path.join(OUT, "ground.npz"), points=f.numpy(), seg=seg.numpy(),
+                        height=height.numpy(), horizon=horizon.numpy(), error=err.numpy(),
+                        pillar_height=pillar_height.numpy(), pillar_min_z=pillar_min_z.numpy())
+    gm = (height < 0.5).numpy()
+    s = seg.numpy()
+    print("ground.npz", f.shape, "removed", gm.sum(), "ground-label coverage", (gm & (s >= 17)).sum() / max((s >= 17).sum(), 1),
+          "foreground removed", (gm & (s > 0) & (s <= 7)).sum() / max(((s > 0) & (s <= 7)).sum(), 1))
