@@ -13,6 +13,37 @@ from . import _lib
 PCS_MAX_K = 32
 PCS_MAX_SEGMENTS = 64
 
+# Optional per-kernel CUDA-event log (bench.py's roofline leg): name -> list of (start, end, meta)
+_EVENT_LOG = None
+
+
+def enable_event_log(on=True):
+    global _EVENT_LOG
+    _EVENT_LOG = {} if on else None
+
+
+def event_log():
+    return _EVENT_LOG
+
+
+class _timed:
+    """Records CUDA events around one kernel launch on the current stream when the event log is enabled."""
+
+    def __init__(self, name, **meta):
+        self.name, self.meta = name, meta
+
+    def __enter__(self):
+        if _EVENT_LOG is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _EVENT_LOG is not None:
+            self.b.record()
+            _EVENT_LOG.setdefault(self.name, []).append((self.a, self.b, self.meta))
+
 
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -93,10 +124,11 @@ class CellGrid:
             self.sorted_pts = torch.empty(max(self.n, 1), 4, dtype=torch.float32, device=dev)
             self.sorted_idx = torch.empty(max(self.n, 1), dtype=torch.int32, device=dev)
             self.counters = torch.empty(4, dtype=torch.int32, device=dev)
-            _lib.check(L.pcs_hash_build(s, _ptr(self.ref), self.n, self.seg_div, self.n_seg, _ptr(self.seg_lo),
-                                        _ptr(self.seg_dims), _f4(self.vs), _ptr(self.table), self.H,
-                                        _ptr(self.sorted_pts), _ptr(self.sorted_idx), _ptr(self.counters)),
-                       "pcs_hash_build")
+            with _timed("hash_build", n=self.n, H=self.H):
+                _lib.check(L.pcs_hash_build(s, _ptr(self.ref), self.n, self.seg_div, self.n_seg, _ptr(self.seg_lo),
+                                            _ptr(self.seg_dims), _f4(self.vs), _ptr(self.table), self.H,
+                                            _ptr(self.sorted_pts), _ptr(self.sorted_idx), _ptr(self.counters)),
+                           "pcs_hash_build")
 
     def check(self):
         """Synchronising check of the device-side error flag (table full / key overflow)."""
@@ -142,7 +174,8 @@ class CellGrid:
             rad_s = float(np.float32(radius))
         if order is not None:
             order = order.int().contiguous()
-        with torch.cuda.device(dev):
+        with torch.cuda.device(dev), _timed("radius_search", n_ref=self.n, n_query=m, K=int(K), lists=bool(want_lists),
+                                            fused_uf=uf_parent is not None):
             _lib.check(_lib.lib().pcs_radius_search(
                 _stream(), _ptr(self.table), self.H, _ptr(self.sorted_pts), _ptr(self.sorted_idx), self.seg_div,
                 self.n_seg, _ptr(self.seg_lo), _ptr(self.seg_dims), _f4(self.vs), _ptr(query), m, _ptr(order),

@@ -155,3 +155,16 @@ def test_oracle_vs_reference_cuda_op_cross_frame(golden_dir):
                                     qmax=[2, 1, 1, 1])
     e = r["cross_edges"]
     assert_neighbor_sets_equal(g["cross_ref"], g["cross_query"], (er, eq), (e[:, 0], e[:, 1]))
+
+
+def test_ground_oracle_matches_reference_python(golden_dir):
+    """oracle/ground_np.py against the reference's own ground_plane_removal (recorded by oracle/gen_golden.py)."""
+    from oracle import ground_np
+    g = _load(golden_dir, "ground.npz")
+    cfg = dict(PILLAR_SIZE=[2, 2], LR=0.01, DECAY_STEPS=[1600], RIGID_WEIGHT=0.5, MAX_NUM_ITERS=10000,
+               TRUNCATE_HEIGHT=[0.5], RANSAC=True, SIGMA2=0.0025, JointOpt=True, K=8)
+    height, horizon, err, ph, pmz = ground_np.ground_plane_removal(g["points"], cfg)
+    assert ph.shape == g["pillar_height"].shape
+    assert np.mean(np.abs(pmz - g["pillar_min_z"]) < 2e-2) > 0.98
+    assert np.mean(np.abs(ph - g["pillar_height"]) < 3e-2) > 0.97
+    assert np.mean((height < 0.5) == (g["height"] < 0.5)) > 0.995
