@@ -155,6 +155,30 @@ int pcs_voxelize_finish(pcs_stream_t s, void *table, int64_t H, const int32_t *u
 int pcs_group_median(pcs_stream_t s, const int64_t *values, const int64_t *inv, int64_t n, const int64_t *offsets,
                      int64_t V, int32_t *cursor_zeroed, int32_t *rows, int64_t *out);
 
+/* ---- ground-stage solvers ---------------------------------------------------------------------
+ * pcs_ground_ransac replaces iterative_reweighted_ransac and the 30-ratio loop around it
+ * (pcdet/models/registration/preprocessors/preprocessor_utils.py:32-80, 147-170) with one cooperative
+ * persistent launch: per super-pillar IRLS plane fits (fp64 moment accumulation, Jacobi 3x3 eigen solve),
+ * the global max|dw| < stopping_delta rule and the best-plane bookkeeping all run on the device.
+ *   vox float4[Nv] (unused,x,y,z) sorted by super-pillar id cidx int32[Nv]; seg_start int32[C+1]
+ *   origin float[C][3] local origins; cmin_z / cmax_z float[C]; ratios float[n_ratios]
+ *   scratch (zero-filled by the caller): w float[Nv], acc double[2][C][10], nhit int32[2][C], gmax uint32[2],
+ *   center / normal float[C][3]
+ *   outputs: best_center float[C][3] (init 0), best_normal float[C][3] (init (0,0,1)), best_conf float[C]
+ *   (init 0), iters_out int32[n_ratios] (optional).
+ * pcs_l1_heightfield replaces l1_minimization (preprocessor_utils.py:313-350): AdamW (torch defaults,
+ * MultiStepLR milestone decay_step, factor lr_gamma) on the X x Y pillar height grid with the reference's
+ * 3-strike stopping rule, up to max_iters iterations in one single-CTA launch.  h is in/out (start point),
+ * m / v zero-filled scratch, info int32[2] = (iterations run, stopped early), loss_out float[1]. */
+int pcs_ground_ransac(pcs_stream_t s, const float *vox, const int32_t *cidx, const int32_t *seg_start,
+                      const float *origin, const float *cmin_z, const float *cmax_z, const float *ratios, int64_t Nv,
+                      int C, int n_ratios, float sigma2, float stopping_delta, int max_iter, float *w, double *acc,
+                      int32_t *nhit, uint32_t *gmax, float *center, float *normal, float *best_center,
+                      float *best_normal, float *best_conf, int32_t *iters_out);
+int pcs_l1_heightfield(pcs_stream_t s, const float *min_z, const float *weight, float *h, float *m, float *v, int X,
+                       int Y, float lr, float lr_gamma, int decay_step, float rigid_weight, int max_iters,
+                       int32_t *info, float *loss_out);
+
 #ifdef __cplusplus
 }
 #endif

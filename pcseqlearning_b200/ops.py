@@ -388,6 +388,66 @@ def group_median(values, inv, num_groups, counts=None):
     return out
 
 
+def ground_ransac(vox_sorted, cidx_sorted, num_coarse, cmin_z, cmax_z, ratios, sigma2, stopping_delta=1e-2,
+                  max_iter=50):
+    """IRLS plane fits of all super-pillars for all height ratios in one cooperative launch
+    (preprocessor_utils.py:32-80 + :147-170).  vox_sorted f32[Nv,4] (.,x,y,z) sorted by cidx_sorted int[Nv].
+    Returns (best_center [C,3], best_normal [C,3], best_conf [C], iters int32[n_ratios])."""
+    vox = _as_points(vox_sorted, "voxels")
+    dev = vox.device
+    Nv, C = vox.shape[0], int(num_coarse)
+    cidx = cidx_sorted.int().contiguous()
+    counts = torch.bincount(cidx_sorted.long(), minlength=C)
+    seg_start = torch.zeros(C + 1, dtype=torch.int32, device=dev)
+    seg_start[1:] = counts.cumsum(0).int()
+    # local origins: first voxel of every super-pillar (empty ones get 0)
+    first = seg_start[:-1].long().clamp(max=max(Nv - 1, 0))
+    origin = torch.where((counts > 0)[:, None], vox[first, 1:], torch.zeros(C, 3, device=dev)).contiguous()
+    ratios = ratios.float().contiguous().to(dev)
+    w = torch.zeros(max(Nv, 1), dtype=torch.float32, device=dev)
+    acc = torch.zeros(2 * C * 10, dtype=torch.float64, device=dev)
+    nhit = torch.zeros(2 * C, dtype=torch.int32, device=dev)
+    gmax = torch.zeros(2, dtype=torch.int32, device=dev)
+    center = torch.zeros(C, 3, dtype=torch.float32, device=dev)
+    normal = torch.zeros(C, 3, dtype=torch.float32, device=dev)
+    best_center = torch.zeros(C, 3, dtype=torch.float32, device=dev)
+    best_normal = torch.zeros(C, 3, dtype=torch.float32, device=dev)
+    best_normal[:, 2] = 1.0
+    best_conf = torch.zeros(C, dtype=torch.float32, device=dev)
+    iters = torch.zeros(ratios.shape[0], dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev), _timed("ground_ransac", Nv=Nv, C=C):
+        _lib.check(_lib.lib().pcs_ground_ransac(
+            _stream(), _ptr(vox), _ptr(cidx), _ptr(seg_start), _ptr(origin), _ptr(cmin_z.float().contiguous()),
+            _ptr(cmax_z.float().contiguous()), _ptr(ratios), Nv, C, int(ratios.shape[0]), float(sigma2),
+            float(stopping_delta), int(max_iter), _ptr(w), _ptr(acc), _ptr(nhit), _ptr(gmax), _ptr(center),
+            _ptr(normal), _ptr(best_center), _ptr(best_normal), _ptr(best_conf), _ptr(iters)), "pcs_ground_ransac")
+    return best_center, best_normal, best_conf, iters
+
+
+L1_MAX_CELLS = 16384
+
+
+def l1_heightfield(min_z, weight, lr, decay_steps, rigid_weight, max_iters, lr_gamma=0.1):
+    """AdamW L1 smoothing of the pillar height grid in one launch (preprocessor_utils.py:313-350).
+    Returns (height [X,Y], iterations run (device int32[2]: iterations, stopped-early))."""
+    X, Y = min_z.shape
+    dev = min_z.device
+    mz = min_z.float().contiguous()
+    wt = weight.float().contiguous().reshape(X, Y)
+    h = torch.zeros(X, Y, dtype=torch.float32, device=dev)
+    m = torch.zeros_like(h)
+    v = torch.zeros_like(h)
+    info = torch.zeros(2, dtype=torch.int32, device=dev)
+    loss = torch.zeros(1, dtype=torch.float32, device=dev)
+    decay = int(decay_steps[0]) if len(decay_steps) else 0
+    assert len(decay_steps) <= 1, "one MultiStepLR milestone is supported on this path"
+    with torch.cuda.device(dev), _timed("l1_heightfield", cells=X * Y):
+        _lib.check(_lib.lib().pcs_l1_heightfield(_stream(), _ptr(mz), _ptr(wt), _ptr(h), _ptr(m), _ptr(v), X, Y,
+                                                 float(lr), float(lr_gamma), decay, float(rigid_weight),
+                                                 int(max_iters), _ptr(info), _ptr(loss)), "pcs_l1_heightfield")
+    return h, info
+
+
 def launch_count():
     return int(_lib.lib().pcs_launch_count())
 

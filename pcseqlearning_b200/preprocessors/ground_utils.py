@@ -73,7 +73,7 @@ def _knn_self(xyz, k):
 
 
 @torch.no_grad()
-def compute_min_height_from_ransac(pillar_dims, num_pillars, voxels, pillars, cfg, window_size=4):
+def compute_min_height_from_ransac(pillar_dims, num_pillars, voxels, pillars, cfg, window_size=4, use_kernels=True):
     """Plane-based estimate of the ground height of every pillar (preprocessor_utils.py:83-272)."""
     X, Y = pillar_dims
     dev = voxels.bxyz.device
@@ -99,17 +99,23 @@ def compute_min_height_from_ransac(pillar_dims, num_pillars, voxels, pillars, cf
     best_normal = c_min_z.new_zeros(num_coarse, 3)
     best_normal[:, -1] = 1.0
     best_center = c_min_z.new_zeros(num_coarse, 3)
-    sigma = cfg.SIGMA2 ** 0.5
-    for ratio in torch.linspace(0.3, 1, 30):
-        cur_z = c_min_z * ratio + c_max_z * (1 - ratio)
-        z_diff = cur_z[cidx] - z
-        w0 = (cfg.SIGMA2 / (z_diff.square() + cfg.SIGMA2)).reshape(-1, 1)
-        err, center, normal = iterative_reweighted_plane_fit(cxyz, cidx, w0, num_coarse, cfg.SIGMA2)
-        num_hit = scatter_sum((err < sigma).float(), cidx, num_coarse)
-        better = best_conf < num_hit
-        best_normal = torch.where(better[:, None], normal, best_normal)
-        best_center = torch.where(better[:, None], center, best_center)
-        best_conf = torch.where(better, num_hit, best_conf)
+    ratios = torch.linspace(0.3, 1, 30)
+    if use_kernels:
+        # all 30 x <=50 IRLS iterations inside one persistent cooperative launch
+        best_center, best_normal, best_conf, _ = ops.ground_ransac(voxels.bxyz[order], cidx, num_coarse, c_min_z,
+                                                                   c_max_z, ratios, cfg.SIGMA2)
+    else:
+        sigma = cfg.SIGMA2 ** 0.5
+        for ratio in ratios:
+            cur_z = c_min_z * ratio + c_max_z * (1 - ratio)
+            z_diff = cur_z[cidx] - z
+            w0 = (cfg.SIGMA2 / (z_diff.square() + cfg.SIGMA2)).reshape(-1, 1)
+            err, center, normal = iterative_reweighted_plane_fit(cxyz, cidx, w0, num_coarse, cfg.SIGMA2)
+            num_hit = scatter_sum((err < sigma).float(), cidx, num_coarse)
+            better = best_conf < num_hit
+            best_normal = torch.where(better[:, None], normal, best_normal)
+            best_center = torch.where(better[:, None], center, best_center)
+            best_conf = torch.where(better, num_hit, best_conf)
 
     # prune planes whose neighbourhood is curved ("Truncated Least Squares", :175-193)
     xyz, normal = best_center, best_normal
@@ -144,9 +150,15 @@ def compute_min_height_from_ransac(pillar_dims, num_pillars, voxels, pillars, cf
     return voxels, pillars
 
 
-def l1_minimization(pillars, pillar_dims, cfg, max_countdown=3):
+def l1_minimization(pillars, pillar_dims, cfg, max_countdown=3, use_kernels=True):
     """AdamW L1 smoothing of the pillar height grid (preprocessor_utils.py:313-350)."""
     X, Y = pillar_dims
+    if use_kernels and X * Y <= ops.L1_MAX_CELLS and X >= 3 and Y >= 3 and len(cfg.DECAY_STEPS) <= 1:
+        # the whole optimisation (<= MAX_NUM_ITERS AdamW steps + stopping rule) in one single-CTA launch
+        pillars["height"], pillars["l1_info"] = ops.l1_heightfield(pillars.min_z, pillars.weight, cfg.LR,
+                                                                   list(cfg.DECAY_STEPS), cfg.RIGID_WEIGHT,
+                                                                   cfg.MAX_NUM_ITERS)
+        return pillars
     weight = pillars.weight.reshape(X, Y)
     min_z = pillars.min_z
     h = torch.nn.Parameter(torch.zeros(X, Y, device=min_z.device), requires_grad=True)
@@ -181,7 +193,7 @@ def l1_minimization(pillars, pillar_dims, cfg, max_countdown=3):
     return pillars
 
 
-def ground_plane_removal(point_fxyz, cfg, warmup=None):
+def ground_plane_removal(point_fxyz, cfg, warmup=None, use_kernels=True):
     """Per-point height above the estimated ground (preprocessor_utils.py:352-419).
 
     Returns (height [N], horizon [N] bool, fitting_error [N], pillar_height [X,Y], pillar_min_z [X,Y]).
@@ -195,9 +207,10 @@ def ground_plane_removal(point_fxyz, cfg, warmup=None):
         pillars.min_z = warmup["pillar_min_z"]
     else:
         if cfg.get("RANSAC", False):
-            voxels, pillars = compute_min_height_from_ransac(pillar_dims, num_pillars, voxels, pillars, cfg)
+            voxels, pillars = compute_min_height_from_ransac(pillar_dims, num_pillars, voxels, pillars, cfg,
+                                                             use_kernels=use_kernels)
         if cfg.get("JointOpt", False):
-            pillars = l1_minimization(pillars, pillar_dims, cfg)
+            pillars = l1_minimization(pillars, pillar_dims, cfg, use_kernels=use_kernels)
         if "height" not in pillars:
             pillars.height = pillars.min_z.clone()
     cx, cy = voxels.pillar_coords[:, 0], voxels.pillar_coords[:, 1]
