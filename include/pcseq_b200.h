@@ -162,7 +162,7 @@ int pcs_group_median(pcs_stream_t s, const int64_t *values, const int64_t *inv, 
  * the global max|dw| < stopping_delta rule and the best-plane bookkeeping all run on the device.
  *   vox float4[Nv] (unused,x,y,z) sorted by super-pillar id cidx int32[Nv]; seg_start int32[C+1]
  *   origin float[C][3] local origins; cmin_z / cmax_z float[C]; ratios float[n_ratios]
- *   scratch (zero-filled by the caller): w float[Nv], acc double[2][C][10], nhit int32[2][C], gmax uint32[2],
+ *   scratch (zero-filled by the caller): w float[Nv], acc double[3][C][10], nhit int32[3][C], gmax uint32[3],
  *   center / normal float[C][3]
  *   outputs: best_center float[C][3] (init 0), best_normal float[C][3] (init (0,0,1)), best_conf float[C]
  *   (init 0), iters_out int32[n_ratios] (optional).

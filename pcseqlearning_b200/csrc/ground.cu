@@ -59,8 +59,9 @@ __device__ void smallest_eigvec3(const double a_in[6], float n_out[3]) {
   n_out[2] = (float)v[2][m];
 }
 
-constexpr int kAcc = 10;       // S0, S1[3], S2[6]
-constexpr int kTileSteps = 8;  // a warp owns 32 x 8 consecutive voxels of the pillar-sorted array
+constexpr int kAcc = 10;         // S0, S1[3], S2[6]
+constexpr int kRansacThreads = 256;
+constexpr int kGroup = 128;      // super-pillars whose planes a block keeps in shared memory at a time
 
 struct RansacArgs {
   const float4 *vox;       // [Nv] (unused, x, y, z) sorted by super-pillar
@@ -71,10 +72,10 @@ struct RansacArgs {
   const float *cmax_z;     // [C]
   const float *ratios;     // [n_ratios]
   float *w;                // [Nv] IRLS weights (scratch)
-  double *acc;             // [2][C][kAcc] ping-pong moment accumulators (zeroed by the caller)
-  int *nhit;               // [2][C] ping-pong hit counters (zeroed by the caller)
-  unsigned int *gmax;      // [2] max |dw| as float bits (zeroed by the caller)
-  float *center;           // [C][3] current plane centre
+  double *acc;             // [3][C][kAcc] rotating moment accumulators (zeroed by the caller)
+  int *nhit;               // [3][C] rotating hit counters (zeroed by the caller)
+  unsigned int *gmax;      // [3] max |dw| as float bits (zeroed by the caller)
+  float *center;           // [C][3] current plane centre (written by the pillar's owner block)
   float *normal;           // [C][3] current plane normal
   float *best_center;      // [C][3] out
   float *best_normal;      // [C][3] out (initialised to (0,0,1) by the caller)
@@ -88,198 +89,248 @@ struct RansacArgs {
   int max_iter;
 };
 
-__device__ __forceinline__ void warp_flush(double *acc10, int hits, int pid, double *acc_buf, int *nhit_buf, int lane) {
+struct Plane {
+  float cx, cy, cz, nx, ny, nz, ox, oy, oz;
+};
+
+// plane of super-pillar p from the accumulated moments: centre = (sum w x)/(sum w + 1e-6), normal = eigenvector of
+// the smallest eigenvalue of mean_i w_i d_i d_i^T (preprocessor_utils.py:47-71); moments are relative to origin[p]
+__device__ __noinline__ void fit_plane(const RansacArgs &A, int p, const double *acc_buf, Plane &pl) {
+  const double *s = acc_buf + (long long)p * kAcc;
+  const double S0 = s[0];
+  const double ox = A.origin[p * 3 + 0], oy = A.origin[p * 3 + 1], oz = A.origin[p * 3 + 2];
+  const double inv = 1.0 / (S0 + 1e-6);
+  const double cax = (s[1] + ox * S0) * inv, cay = (s[2] + oy * S0) * inv, caz = (s[3] + oz * S0) * inv;
+  const double cx = cax - ox, cy = cay - oy, cz = caz - oz;
+  const int n = A.seg_start[p + 1] - A.seg_start[p];
+  const double invn = 1.0 / (double)(n > 0 ? n : 1);
+  double cov[6];
+  cov[0] = (s[4] - 2.0 * cx * s[1] + S0 * cx * cx) * invn;
+  cov[1] = (s[5] - cx * s[2] - cy * s[1] + S0 * cx * cy) * invn;
+  cov[2] = (s[6] - cx * s[3] - cz * s[1] + S0 * cx * cz) * invn;
+  cov[3] = (s[7] - 2.0 * cy * s[2] + S0 * cy * cy) * invn;
+  cov[4] = (s[8] - cy * s[3] - cz * s[2] + S0 * cy * cz) * invn;
+  cov[5] = (s[9] - 2.0 * cz * s[3] + S0 * cz * cz) * invn;
+  float nrm[3];
+  smallest_eigvec3(cov, nrm);
+  pl.cx = (float)cax;
+  pl.cy = (float)cay;
+  pl.cz = (float)caz;
+  pl.nx = nrm[0];
+  pl.ny = nrm[1];
+  pl.nz = nrm[2];
+  pl.ox = (float)ox;
+  pl.oy = (float)oy;
+  pl.oz = (float)oz;
+}
+
+__device__ __forceinline__ void warp_flush(float *acc10, int &hits, int pid, double *acc_buf, int *nhit_buf, int lane) {
 #pragma unroll
   for (int k = 0; k < kAcc; k++) {
-    double v = acc10[k];
+    double v = (double)acc10[k];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
     if (lane == 0 && v != 0.0) atomicAdd(acc_buf + (long long)pid * kAcc + k, v);
-    acc10[k] = 0.0;
+    acc10[k] = 0.f;
   }
   int h = hits;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) h += __shfl_down_sync(0xffffffffu, h, o);
   if (lane == 0 && h != 0) atomicAdd(nhit_buf + pid, h);
+  hits = 0;
 }
 
-// One sweep over the voxels: evaluates the planes of the current iteration (new weights, |dw|, hits) and
-// accumulates the weighted moments the NEXT plane fit needs.  first = weights come from the height prior.
-__device__ void ransac_sweep(const RansacArgs &A, bool first, float ratio, double *acc_buf, int *nhit_buf,
-                             unsigned int *gmax_slot) {
-  const int lane = threadIdx.x & 31;
-  const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  const long long tile = 32LL * kTileSteps;
-  const long long ntiles = (A.Nv + tile - 1) / tile;
+// One IRLS half-step of a block over its contiguous voxel range [v0, v1):
+//   fit the planes of the super-pillars in the range from acc_fit (skipped when `first`: weights come from
+//   the height prior), evaluate them on every voxel (new weight, |dw|, hit) and accumulate the moments of the
+//   NEXT fit into acc_next.  Pillars are handled in groups of kGroup whose planes live in shared memory.
+//   The block that owns a pillar (holds its first voxel) publishes the plane and clears the spare buffers.
+__device__ void ransac_step(const RansacArgs &A, long long v0, long long v1, bool first, float ratio,
+                            const double *acc_fit, double *acc_next, int *nhit_next, unsigned int *gmax_next,
+                            double *acc_spare, int *nhit_spare, Plane *s_plane) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nwarp = kRansacThreads / 32;
   const float sigma = sqrtf(A.sigma2);
   float dmax = 0.f;
-  for (long long t = warp_global; t < ntiles; t += nwarps) {
-    double acc[kAcc];
-#pragma unroll
-    for (int k = 0; k < kAcc; k++) acc[k] = 0.0;
-    int hits = 0;
-    int cur = -1;
-    for (int s = 0; s < kTileSteps; s++) {
-      const long long i = t * tile + s * 32 + lane;
-      const bool valid = i < A.Nv;
-      int pid = -1;
-      float wnew = 0.f;
-      float xr = 0.f, yr = 0.f, zr = 0.f;
-      int hit = 0;
-      if (valid) {
-        pid = A.cidx[i];
-        const float4 p = A.vox[i];
-        if (first) {
-          const float cur_z = A.cmin_z[pid] * ratio + A.cmax_z[pid] * (1.0f - ratio);
-          const float zd = cur_z - p.w;
-          wnew = A.sigma2 / (zd * zd + A.sigma2);
+  if (v1 > v0) {
+    const int p_first = A.cidx[v0], p_last = A.cidx[v1 - 1];
+    for (int g0 = p_first; g0 <= p_last; g0 += kGroup) {
+      const int g1 = min(g0 + kGroup, p_last + 1);  // pillars [g0, g1)
+      __syncthreads();
+      for (int p = g0 + threadIdx.x; p < g1; p += kRansacThreads) {
+        Plane pl;
+        if (!first) {
+          fit_plane(A, p, acc_fit, pl);
         } else {
-          const float dx = p.y - A.center[pid * 3 + 0], dy = p.z - A.center[pid * 3 + 1],
-                      dz = p.w - A.center[pid * 3 + 2];
-          const float err = fabsf(dx * A.normal[pid * 3 + 0] + dy * A.normal[pid * 3 + 1] + dz * A.normal[pid * 3 + 2]);
-          hit = err < sigma;
-          const float nw = A.sigma2 / (err * err + A.sigma2);
-          const float dw = 0.25f / (dx * dx + dy * dy + dz * dz + 0.25f);
-          wnew = nw * dw;
-          dmax = fmaxf(dmax, fabsf(wnew - A.w[i]));
+          pl.ox = A.origin[p * 3 + 0];
+          pl.oy = A.origin[p * 3 + 1];
+          pl.oz = A.origin[p * 3 + 2];
+          pl.cx = A.cmin_z[p] * ratio + A.cmax_z[p] * (1.0f - ratio);  // prior height (preprocessor_utils.py:148)
+          pl.cy = pl.cz = pl.nx = pl.ny = pl.nz = 0.f;
         }
-        A.w[i] = wnew;
-        xr = p.y - A.origin[pid * 3 + 0];
-        yr = p.z - A.origin[pid * 3 + 1];
-        zr = p.w - A.origin[pid * 3 + 2];
-      }
-      const int p0 = __shfl_sync(0xffffffffu, pid, 0);
-      const bool uniform = __all_sync(0xffffffffu, (!valid) || pid == p0) && p0 >= 0;
-      if (uniform) {
-        if (p0 != cur) {
-          if (cur >= 0) warp_flush(acc, hits, cur, acc_buf, nhit_buf, lane);
-          hits = 0;
-          cur = p0;
-        }
-        if (valid) {
-          const double w = wnew, x = xr, y = yr, z = zr;
-          acc[0] += w;
-          acc[1] += w * x;
-          acc[2] += w * y;
-          acc[3] += w * z;
-          acc[4] += w * x * x;
-          acc[5] += w * x * y;
-          acc[6] += w * x * z;
-          acc[7] += w * y * y;
-          acc[8] += w * y * z;
-          acc[9] += w * z * z;
-          hits += hit;
-        }
-      } else {
-        if (cur >= 0) warp_flush(acc, hits, cur, acc_buf, nhit_buf, lane);
-        hits = 0;
-        cur = -1;
-        if (valid) {  // a pillar boundary inside this step: per-lane atomics
-          const double w = wnew, x = xr, y = yr, z = zr;
-          double *b = acc_buf + (long long)pid * kAcc;
-          atomicAdd(b + 0, w);
-          atomicAdd(b + 1, w * x);
-          atomicAdd(b + 2, w * y);
-          atomicAdd(b + 3, w * z);
-          atomicAdd(b + 4, w * x * x);
-          atomicAdd(b + 5, w * x * y);
-          atomicAdd(b + 6, w * x * z);
-          atomicAdd(b + 7, w * y * y);
-          atomicAdd(b + 8, w * y * z);
-          atomicAdd(b + 9, w * z * z);
-          if (hit) atomicAdd(nhit_buf + pid, 1);
+        s_plane[p - g0] = pl;
+        const long long ps = A.seg_start[p];
+        if (ps >= v0 && ps < v1 && A.seg_start[p + 1] > ps) {  // owner of a non-empty pillar
+          if (!first) {
+            A.center[p * 3 + 0] = pl.cx;
+            A.center[p * 3 + 1] = pl.cy;
+            A.center[p * 3 + 2] = pl.cz;
+            A.normal[p * 3 + 0] = pl.nx;
+            A.normal[p * 3 + 1] = pl.ny;
+            A.normal[p * 3 + 2] = pl.nz;
+          }
+          for (int k = 0; k < kAcc; k++) acc_spare[(long long)p * kAcc + k] = 0.0;
+          nhit_spare[p] = 0;
         }
       }
+      __syncthreads();
+      // voxels of this pillar group inside the block's range
+      const long long a = max(v0, (long long)A.seg_start[g0]);
+      const long long b = min(v1, (long long)A.seg_start[g1]);
+      float acc[kAcc];
+#pragma unroll
+      for (int k = 0; k < kAcc; k++) acc[k] = 0.f;
+      int hits = 0;
+      int cur = -1;
+      constexpr int U = 4;  // warp steps whose loads are issued together (memory-level parallelism)
+      for (long long base0 = a + warp * 32; base0 < b; base0 += (long long)U * nwarp * 32) {
+        int pidv[U];
+        float4 pv[U];
+        float wold[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const long long i = base0 + (long long)u * nwarp * 32 + lane;
+          pidv[u] = -1;
+          if (i < b) {
+            pidv[u] = __ldg(A.cidx + i);
+            pv[u] = __ldg(A.vox + i);
+            wold[u] = first ? 0.f : A.w[i];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const long long i = base0 + (long long)u * nwarp * 32 + lane;
+          const int pid = pidv[u];
+          const bool valid = pid >= 0;
+          float wnew = 0.f, xr = 0.f, yr = 0.f, zr = 0.f;
+          int hit = 0;
+          if (valid) {
+            const float4 p = pv[u];
+            const Plane &pl = s_plane[pid - g0];
+            if (first) {
+              const float zd = pl.cx - p.w;
+              wnew = A.sigma2 / (zd * zd + A.sigma2);
+            } else {
+              const float dx = p.y - pl.cx, dy = p.z - pl.cy, dz = p.w - pl.cz;
+              const float err = fabsf(dx * pl.nx + dy * pl.ny + dz * pl.nz);
+              hit = err < sigma;
+              const float nw = A.sigma2 / (err * err + A.sigma2);
+              const float dw = 0.25f / (dx * dx + dy * dy + dz * dz + 0.25f);
+              wnew = nw * dw;
+              dmax = fmaxf(dmax, fabsf(wnew - wold[u]));
+            }
+            A.w[i] = wnew;
+            xr = p.y - pl.ox;
+            yr = p.z - pl.oy;
+            zr = p.w - pl.oz;
+          }
+          const int pl0 = __shfl_sync(0xffffffffu, pid, 0);
+          const bool uniform = __all_sync(0xffffffffu, (!valid) || pid == pl0) && pl0 >= 0;
+          if (uniform) {
+            if (pl0 != cur) {
+              if (cur >= 0) warp_flush(acc, hits, cur, acc_next, nhit_next, lane);
+              cur = pl0;
+            }
+            if (valid) {
+              const float wx = wnew * xr, wy = wnew * yr, wz = wnew * zr;
+              acc[0] += wnew;
+              acc[1] += wx;
+              acc[2] += wy;
+              acc[3] += wz;
+              acc[4] += wx * xr;
+              acc[5] += wx * yr;
+              acc[6] += wx * zr;
+              acc[7] += wy * yr;
+              acc[8] += wy * zr;
+              acc[9] += wz * zr;
+              hits += hit;
+            }
+          } else if (__any_sync(0xffffffffu, valid)) {
+            if (cur >= 0) warp_flush(acc, hits, cur, acc_next, nhit_next, lane);
+            cur = -1;
+            if (valid) {  // a pillar boundary inside this warp step: per-lane atomics
+              const double w = wnew, x = xr, y = yr, z = zr;
+              double *d = acc_next + (long long)pid * kAcc;
+              atomicAdd(d + 0, w);
+              atomicAdd(d + 1, w * x);
+              atomicAdd(d + 2, w * y);
+              atomicAdd(d + 3, w * z);
+              atomicAdd(d + 4, w * x * x);
+              atomicAdd(d + 5, w * x * y);
+              atomicAdd(d + 6, w * x * z);
+              atomicAdd(d + 7, w * y * y);
+              atomicAdd(d + 8, w * y * z);
+              atomicAdd(d + 9, w * z * z);
+              if (hit) atomicAdd(nhit_next + pid, 1);
+            }
+          }
+        }
+      }
+      if (cur >= 0) warp_flush(acc, hits, cur, acc_next, nhit_next, lane);
     }
-    if (cur >= 0) warp_flush(acc, hits, cur, acc_buf, nhit_buf, lane);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) dmax = fmaxf(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
-  if (lane == 0 && dmax > 0.f) atomicMax(gmax_slot, __float_as_uint(dmax));
+  if (lane == 0 && dmax > 0.f) atomicMax(gmax_next, __float_as_uint(dmax));
 }
 
-// plane fit of every super-pillar from the accumulated moments; also clears the other ping-pong buffer
-__device__ void ransac_fit(const RansacArgs &A, const double *acc_buf, double *acc_other, int *nhit_other) {
-  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long nthreads = (long long)gridDim.x * blockDim.x;
-  for (long long p = tid; p < A.C; p += nthreads) {
-    const double *s = acc_buf + p * kAcc;
-    const double S0 = s[0];
-    const double ox = A.origin[p * 3 + 0], oy = A.origin[p * 3 + 1], oz = A.origin[p * 3 + 2];
-    const double inv = 1.0 / (S0 + 1e-6);
-    // centre in absolute coordinates, (sum w x) / (sum w + 1e-6), and relative to the local origin
-    const double cax = (s[1] + ox * S0) * inv, cay = (s[2] + oy * S0) * inv, caz = (s[3] + oz * S0) * inv;
-    const double cx = cax - ox, cy = cay - oy, cz = caz - oz;
-    int n = A.seg_start[p + 1] - A.seg_start[p];
-    const double invn = 1.0 / (double)(n > 0 ? n : 1);
-    double cov[6];
-    cov[0] = (s[4] - 2.0 * cx * s[1] + S0 * cx * cx) * invn;
-    cov[1] = (s[5] - cx * s[2] - cy * s[1] + S0 * cx * cy) * invn;
-    cov[2] = (s[6] - cx * s[3] - cz * s[1] + S0 * cx * cz) * invn;
-    cov[3] = (s[7] - 2.0 * cy * s[2] + S0 * cy * cy) * invn;
-    cov[4] = (s[8] - cy * s[3] - cz * s[2] + S0 * cy * cz) * invn;
-    cov[5] = (s[9] - 2.0 * cz * s[3] + S0 * cz * cz) * invn;
-    float nrm[3];
-    smallest_eigvec3(cov, nrm);
-    A.center[p * 3 + 0] = (float)cax;
-    A.center[p * 3 + 1] = (float)cay;
-    A.center[p * 3 + 2] = (float)caz;
-    A.normal[p * 3 + 0] = nrm[0];
-    A.normal[p * 3 + 1] = nrm[1];
-    A.normal[p * 3 + 2] = nrm[2];
-  }
-  for (long long k = tid; k < (long long)A.C * kAcc; k += nthreads) acc_other[k] = 0.0;
-  for (long long k = tid; k < A.C; k += nthreads) nhit_other[k] = 0;
-}
-
-__global__ void __launch_bounds__(256) ground_ransac_kernel(RansacArgs A) {
+__global__ void __launch_bounds__(kRansacThreads, 3) ground_ransac_kernel(RansacArgs A) {
   cg::grid_group grid = cg::this_grid();
-  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long nthreads = (long long)gridDim.x * blockDim.x;
-  int buf = 0;  // accumulators being filled by the sweep
+  __shared__ Plane s_plane[kGroup];
+  // contiguous, 32-aligned voxel range of this block
+  const long long per = (((A.Nv + gridDim.x - 1) / gridDim.x) + 31) / 32 * 32;
+  const long long v0 = min((long long)blockIdx.x * per, A.Nv), v1 = min(v0 + per, A.Nv);
+  const long long accN = (long long)A.C * kAcc;
   for (int r = 0; r < A.n_ratios; r++) {
     const float ratio = A.ratios[r];
-    // weights from the height prior + moments of the first fit
-    ransac_sweep(A, true, ratio, A.acc + (long long)buf * A.C * kAcc, A.nhit + buf * A.C, A.gmax + 0);
+    // weights from the height prior; moments of fit 0 -> buffer 0 (buffers 1 and 2 are clear)
+    ransac_step(A, v0, v1, true, ratio, nullptr, A.acc, A.nhit, A.gmax + 0, A.acc + 2 * accN, A.nhit + 2 * A.C, s_plane);
     grid.sync();
-    int it = 0;
+    int it = 0, last_eval = 0;
     for (; it < A.max_iter; it++) {
-      // fit planes from acc[buf]; clear acc[buf^1], nhit[buf^1]
-      ransac_fit(A, A.acc + (long long)buf * A.C * kAcc, A.acc + (long long)(buf ^ 1) * A.C * kAcc,
-                 A.nhit + (buf ^ 1) * A.C);
-      if (tid == 0) A.gmax[(it + 1) & 1] = 0u;  // slot of the next sweep
+      const int bf = it % 3, bn = (it + 1) % 3, bs = (it + 2) % 3;
+      if (blockIdx.x == 0 && threadIdx.x == 0) A.gmax[bs] = 0u;
+      ransac_step(A, v0, v1, false, ratio, A.acc + bf * accN, A.acc + bn * accN, A.nhit + bn * A.C, A.gmax + bn,
+                  A.acc + bs * accN, A.nhit + bs * A.C, s_plane);
+      last_eval = bn;
       grid.sync();
-      // evaluate the planes (new weights, max |dw|, hits) and accumulate the next fit's moments
-      ransac_sweep(A, false, ratio, A.acc + (long long)(buf ^ 1) * A.C * kAcc, A.nhit + (buf ^ 1) * A.C,
-                   A.gmax + ((it + 1) & 1));
-      buf ^= 1;
-      grid.sync();
-      const float dmax = __uint_as_float(A.gmax[(it + 1) & 1]);
-      if (dmax < A.stopping_delta) {
+      if (__uint_as_float(A.gmax[bn]) < A.stopping_delta) {
         ++it;
         break;
       }
     }
-    if (tid == 0 && A.iters_out) A.iters_out[r] = it;
-    // keep the planes that explain the most voxels (preprocessor_utils.py:160-170); nhit[buf] holds the hits of
-    // the last evaluated planes
-    for (long long p = tid; p < A.C; p += nthreads) {
-      const float nh = (float)A.nhit[buf * A.C + p];
-      if (A.best_conf[p] < nh) {
-        A.best_conf[p] = nh;
-        for (int k = 0; k < 3; k++) {
-          A.best_normal[p * 3 + k] = A.normal[p * 3 + k];
-          A.best_center[p * 3 + k] = A.center[p * 3 + k];
+    if (blockIdx.x == 0 && threadIdx.x == 0 && A.iters_out) A.iters_out[r] = it;
+    // owners keep the plane that explains the most voxels (preprocessor_utils.py:160-170) and clear all buffers
+    if (v1 > v0) {
+      const int p_first = A.cidx[v0], p_last = A.cidx[v1 - 1];
+      for (int p = p_first + threadIdx.x; p <= p_last; p += kRansacThreads) {
+        const long long ps = A.seg_start[p];
+        if (!(ps >= v0 && ps < v1 && A.seg_start[p + 1] > ps)) continue;
+        const float nh = (float)A.nhit[last_eval * A.C + p];
+        if (A.best_conf[p] < nh) {
+          A.best_conf[p] = nh;
+          for (int k = 0; k < 3; k++) {
+            A.best_normal[p * 3 + k] = A.normal[p * 3 + k];
+            A.best_center[p * 3 + k] = A.center[p * 3 + k];
+          }
+        }
+        for (int bsel = 0; bsel < 3; bsel++) {
+          for (int k = 0; k < kAcc; k++) A.acc[bsel * accN + (long long)p * kAcc + k] = 0.0;
+          A.nhit[bsel * A.C + p] = 0;
         }
       }
     }
-    grid.sync();
-    // reset the accumulators for the next ratio
-    for (long long k = tid; k < 2LL * A.C * kAcc; k += nthreads) A.acc[k] = 0.0;
-    for (long long k = tid; k < 2LL * A.C; k += nthreads) A.nhit[k] = 0;
-    if (tid == 0) A.gmax[0] = A.gmax[1] = 0u;
-    buf = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) A.gmax[0] = A.gmax[1] = A.gmax[2] = 0u;
     grid.sync();
   }
 }
@@ -334,7 +385,7 @@ __global__ void __launch_bounds__(1024) l1_heightfield_kernel(L1Args A) {
     // ---- loss and gradient (gather form) ------------------------------------------------------------
     double lsum = 0.0;
     // each thread keeps the gradients of its cells in registers across the sync below
-    float g[16];
+    float g[64];
     int nc = 0;
     for (int c = threadIdx.x; c < P; c += blockDim.x, nc++) {
       const int i = c / Y, j = c - i * Y;
@@ -399,7 +450,7 @@ __global__ void __launch_bounds__(1024) l1_heightfield_kernel(L1Args A) {
         const float t = (HH(i + 2, j - 2) - 2.f * HH(i + 1, j - 1) + hc) * WW(i + 1, j - 1);
         grad += sgnf(t) * WW(i + 1, j - 1) * k3;
       }
-      g[nc] = grad;  // nc < 16 because P <= 16384 (checked by the host wrapper)
+      g[nc] = grad;  // nc < 64 because P <= 65536 (checked by the host wrapper)
       lsum += l;
     }
     // block reduction of the loss
@@ -492,18 +543,16 @@ int pcs_ground_ransac(pcs_stream_t s, const float *vox, const int32_t *cidx, con
   int dev = 0, sms = 148, per_sm = 1;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ground_ransac_kernel, 256, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ground_ransac_kernel, kRansacThreads, 0);
   if (per_sm < 1) per_sm = 1;
   if (per_sm > 4) per_sm = 4;
-  long long want = (Nv + 256LL * kTileSteps - 1) / (256LL * kTileSteps);
-  long long minb = (C + 255) / 256;
-  long long blocks = want < minb ? minb : want;
+  long long blocks = (Nv + 2047) / 2048;  // at least ~2k voxels per block
   long long cap = (long long)sms * per_sm;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   void *args[] = {&A};
-  cudaError_t e = cudaLaunchCooperativeKernel((void *)ground_ransac_kernel, dim3((unsigned)blocks), dim3(256), args, 0,
-                                              as_stream(s));
+  cudaError_t e = cudaLaunchCooperativeKernel((void *)ground_ransac_kernel, dim3((unsigned)blocks),
+                                              dim3(kRansacThreads), args, 0, as_stream(s));
   g_launches++;
   if (e != cudaSuccess) return set_error((int)e, "ground_ransac_kernel (cooperative launch)");
   return check_launch("ground_ransac_kernel");
@@ -512,8 +561,8 @@ int pcs_ground_ransac(pcs_stream_t s, const float *vox, const int32_t *cidx, con
 int pcs_l1_heightfield(pcs_stream_t s, const float *min_z, const float *weight, float *h, float *m, float *v, int X,
                        int Y, float lr, float lr_gamma, int decay_step, float rigid_weight, int max_iters,
                        int32_t *info, float *loss_out) {
-  if (X < 3 || Y < 3 || (long long)X * Y > 16384 || !min_z || !weight || !h || !m || !v || !info || !loss_out)
-    return set_error(PCS_ERR_BAD_ARG, "pcs_l1_heightfield: bad args (3 <= X,Y and X*Y <= 16384)");
+  if (X < 3 || Y < 3 || (long long)X * Y > 65536 || !min_z || !weight || !h || !m || !v || !info || !loss_out)
+    return set_error(PCS_ERR_BAD_ARG, "pcs_l1_heightfield: bad args (3 <= X,Y and X*Y <= 65536)");
   L1Args A;
   A.min_z = min_z;
   A.weight = weight;

@@ -405,9 +405,9 @@ def ground_ransac(vox_sorted, cidx_sorted, num_coarse, cmin_z, cmax_z, ratios, s
     origin = torch.where((counts > 0)[:, None], vox[first, 1:], torch.zeros(C, 3, device=dev)).contiguous()
     ratios = ratios.float().contiguous().to(dev)
     w = torch.zeros(max(Nv, 1), dtype=torch.float32, device=dev)
-    acc = torch.zeros(2 * C * 10, dtype=torch.float64, device=dev)
-    nhit = torch.zeros(2 * C, dtype=torch.int32, device=dev)
-    gmax = torch.zeros(2, dtype=torch.int32, device=dev)
+    acc = torch.zeros(3 * C * 10, dtype=torch.float64, device=dev)
+    nhit = torch.zeros(3 * C, dtype=torch.int32, device=dev)
+    gmax = torch.zeros(4, dtype=torch.int32, device=dev)
     center = torch.zeros(C, 3, dtype=torch.float32, device=dev)
     normal = torch.zeros(C, 3, dtype=torch.float32, device=dev)
     best_center = torch.zeros(C, 3, dtype=torch.float32, device=dev)
@@ -424,7 +424,7 @@ def ground_ransac(vox_sorted, cidx_sorted, num_coarse, cmin_z, cmax_z, ratios, s
     return best_center, best_normal, best_conf, iters
 
 
-L1_MAX_CELLS = 16384
+L1_MAX_CELLS = 65536
 
 
 def l1_heightfield(min_z, weight, lr, decay_steps, rigid_weight, max_iters, lr_gamma=0.1):
