@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _lib = None
 
 c_void_p, c_int, c_int64, c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
+c_double = ctypes.c_double
 
 # name -> (restype, argtypes); mirrors include/pcseq_b200.h one to one
 _SIGNATURES = {
@@ -21,7 +22,7 @@ _SIGNATURES = {
     "pcs_reset_launch_count": (None, []),
     "pcs_bounds_init": (c_int, [c_void_p, c_void_p, c_int]),
     "pcs_bounds_update": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
-    "pcs_grid_params": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "pcs_grid_params": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "pcs_voxel_keys": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_void_p]),
     "pcs_hash_build": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -50,6 +51,11 @@ _SIGNATURES = {
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pcs_l1_heightfield": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float,
                                    c_float, c_int, c_float, c_int, c_void_p, c_void_p]),
+    "pcs_register_icp": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
+                                 c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_double, c_int, c_double,
+                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_void_p, c_void_p]),
     "pcs_group_median": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p,
                                  c_void_p]),
 }

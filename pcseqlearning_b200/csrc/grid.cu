@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(256) bounds_update_kernel(const float4 *__rest
 
 // lo = min - 2*vs ; hi = max + 2*vs ; dims = rint((hi - lo)/vs) + 3   (graph_utils.py:172-176, fp32)
 __global__ void grid_params_kernel(const unsigned int *__restrict__ bounds, int n_seg, float vs0, float vs1,
-                                   float vs2, float vs3, float *__restrict__ seg_lo,
+                                   float vs2, float vs3, int pad, float *__restrict__ seg_lo,
                                    long long *__restrict__ seg_dims) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_seg * 4) return;
@@ -102,8 +102,10 @@ __global__ void grid_params_kernel(const unsigned int *__restrict__ bounds, int 
   float two_vs = __fmul_rn(vs, 2.0f);
   float lo = __fsub_rn(ord2f(omin), two_vs);
   float hi = __fadd_rn(ord2f(omax), two_vs);
-  seg_lo[i] = lo;
-  seg_dims[i] = (long long)rintf(__fdiv_rn(__fsub_rn(hi, lo), vs)) + 3;
+  // pad > 0 (persistent ICP): `pad` extra cells of margin on every side, for point sets that move after the
+  // grid has been laid out; pad == 0 is the reference geometry bit for bit
+  seg_lo[i] = pad ? __fsub_rn(lo, __fmul_rn(vs, (float)pad)) : lo;
+  seg_dims[i] = (long long)rintf(__fdiv_rn(__fsub_rn(hi, lo), vs)) + 3 + 2 * pad;
 }
 
 __global__ void __launch_bounds__(256) voxel_keys_kernel(const float4 *__restrict__ pts, long long n, SegGeom g,
@@ -302,11 +304,11 @@ int pcs_bounds_update(pcs_stream_t s, const float *pts, int64_t n, int seg_div, 
   return 0;
 }
 
-int pcs_grid_params(pcs_stream_t s, const uint32_t *bounds, int n_seg, const float *vs, float *seg_lo,
+int pcs_grid_params(pcs_stream_t s, const uint32_t *bounds, int n_seg, const float *vs, int pad, float *seg_lo,
                     int64_t *seg_dims) {
   if (!bounds || !vs || !seg_lo || !seg_dims || n_seg < 1 || n_seg > PCS_MAX_SEGMENTS)
     return set_error(PCS_ERR_BAD_ARG, "pcs_grid_params: bad args");
-  PCS_LAUNCH(grid_params_kernel, 1, 256, 0, as_stream(s), bounds, n_seg, vs[0], vs[1], vs[2], vs[3], seg_lo,
+  PCS_LAUNCH(grid_params_kernel, 1, 256, 0, as_stream(s), bounds, n_seg, vs[0], vs[1], vs[2], vs[3], pad, seg_lo,
              (long long *)seg_dims);
   return 0;
 }
