@@ -1,0 +1,93 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: window planning, halos, anchors and the collective that
+turns window-local component ids into the reference's sequence-global numbering."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from pcseqlearning_b200 import parallel
+
+
+def test_frame_windows_cover_and_align():
+    for num_frames in (16, 198, 40, 7, 400):
+        for world in (1, 2, 4, 8):
+            w = parallel.frame_windows(num_frames, world)
+            assert len(w) == world
+            covered = []
+            for s, e in w:
+                assert s % 40 == 0 or s == num_frames
+                covered += list(range(s, e))
+            assert covered == list(range(num_frames))
+            anchors = sum((parallel.anchors_of_window(x) for x in w), [])
+            assert anchors == list(range(0, num_frames, 8))
+            for x in w:
+                hs, he = parallel.halo_window(x, num_frames)
+                for a in parallel.anchors_of_window(x):
+                    assert hs <= max(0, a - 8) and min(num_frames, a + 9) <= he
+
+
+def test_sequences_round_robin():
+    got = sorted(sum((parallel.sequences_of_rank(64, r, 8) for r in range(8)), []))
+    assert got == list(range(64))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, num_frames, workdir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import cpu_ops as oracle
+    data = np.load(os.path.join(workdir, "in.npz"))
+    pts_all, labels_ref = data["points"], data["labels"]
+    frames = np.rint(pts_all[:, 0]).astype(np.int64)
+    win = parallel.frame_windows(num_frames, world)[rank]
+    mask = (frames >= win[0]) & (frames < win[1])
+    pts = pts_all[mask]
+    if pts.shape[0] > 0:
+        # the rank clusters only its own window (CPU oracle stands in for the GPU kernels in this host-logic test)
+        lab, _ = oracle.propose_clusters(pts, 0.75)
+        n_chunks = (win[1] - win[0] + 9) // 10
+        f = np.rint(pts[:, 0]).astype(np.int64)
+        n_comp = np.array([len(np.unique(lab[(f // 10) == (win[0] // 10 + c)])) for c in range(n_chunks)])
+    else:
+        lab, n_comp, f = np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0, np.int64)
+    glob, counts = parallel.globalize_component_ids(torch.from_numpy(lab), torch.from_numpy(f), torch.from_numpy(n_comp),
+                                                    win, num_frames)
+    ok = np.array_equal(glob.numpy(), labels_ref[mask])
+    t = parallel.max_over_ranks(10.0 + rank, "cpu")
+    res = torch.tensor([int(ok), int(t == 10.0 + world - 1), int(counts.sum().item() == labels_ref.max() + 1)])
+    dist.all_reduce(res, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        np.save(os.path.join(workdir, "result.npy"), res.numpy())
+    dist.destroy_process_group()
+
+
+def test_globalize_component_ids_two_ranks(golden_dir, tmp_path):
+    """Two ranks cluster disjoint frame windows; after the count exchange their ids equal the single-process ids."""
+    from oracle import cpu_ops as oracle
+    g = np.load(os.path.join(golden_dir, "proposal.npz"))
+    # stretch the 13 golden frames over 2 windows of 40 frames so that both ranks own chunks
+    pts = g["points"].copy()
+    pts[:, 0] = np.rint(pts[:, 0]) * 5
+    num_frames = int(pts[:, 0].max()) + 1
+    labels_ref, _ = oracle.propose_clusters(pts, 0.75)
+    np.savez(os.path.join(tmp_path, "in.npz"), points=pts, labels=labels_ref)
+    port = _free_port()
+    ctx = mp.get_context("spawn")  # fork after the OpenMP oracle has run in the parent would hang
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, num_frames, str(tmp_path))) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert np.load(os.path.join(tmp_path, "result.npy")).tolist() == [1, 1, 1]
