@@ -91,14 +91,19 @@ int pcs_hash_build(pcs_stream_t s, const float *pts, int64_t n, int seg_div, int
  *   nbr_idx    int32[m][K] reference row indices, ascending (d2, index); may be NULL when uf_parent set
  *   nbr_d2     float[m][K] optional
  *   nbr_cnt    int32[m] = min(#accepted, K)
- *   uf_parent  optional int32[n_ref == m]: union-find forest; when given, every (query, neighbour)
- *              pair is united in-kernel (fused connected components, no edge list materialised). */
+ *   uf_parents (host) array of n_uf <= 3 device forests int32[n_ref == m]; forest k receives every (query,
+ *              neighbour) pair with d2 <= uf_r2[k], united in-kernel (fused connected components, no edge list
+ *              materialised); with uf_need_full[k] set it is only fed by queries whose list is full (count == K):
+ *              for those the K nearest within this radius are also the K nearest within any larger radius, which
+ *              is how ONE fine search serves several proposal radii (multi-radius search).
+ *   skip_full_cnt optional int32[m]: counts of a previous (finer) pass; queries with count >= K are skipped. */
 int pcs_radius_search(pcs_stream_t s, const pcs_slot_t *table, int64_t H, const float *sorted_pts,
                       const int32_t *sorted_idx, int seg_div, int n_seg, const float *seg_lo,
                       const int64_t *seg_dims, const float *vs, const float *queries, int64_t m,
                       const int32_t *order, const int *qmin, const int *qmax, const float *radius,
                       float radius_scalar, int K, int32_t *nbr_idx, float *nbr_d2, int32_t *nbr_cnt,
-                      int32_t *uf_parent);
+                      int32_t *const *uf_parents, const float *uf_r2, const int *uf_need_full, int n_uf,
+                      const int32_t *skip_full_cnt);
 
 /* Exclusive scan int32 -> int64 with the grand total at out[n] (out has n+1 entries).
  * Replaces `cumsum(degree) - degree` (torch_hash_kernel.cu:534-538) without the two blocking .item(). */

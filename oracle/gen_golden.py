@@ -167,6 +167,7 @@ def main():
     gen_proposal()
     gen_registration()
     gen_ground()
+    gen_tracking()
 
 
 if __name__ == "__main__":
@@ -192,3 +193,50 @@ def gen_ground():
     s = seg.numpy()
     print("ground.npz", f.shape, "removed", gm.sum(), "ground-label coverage", (gm & (s >= 17)).sum() / max((s >= 17).sum(), 1),
           "foreground removed", (gm & (s > 0) & (s <= 7)).sum() / max(((s > 0) & (s <= 7)).sum(), 1))
+
+
+def gen_tracking():
+    """ClusterTracking.track_frame (cluster_tracking.py:430-787) for one anchor frame of a small 17-frame scene,
+    run by the reference's own code (CPU)."""
+    import time
+    ct = R.load("pcdet.models.registration.preprocessors.cluster_tracking")
+    cu = R.load("pcdet.utils.common_utils")
+    from . import cpu_ops as ops
+    b, f, seg = _scene(8, 17, 24, 600)
+    keep = seg < 17
+    f, seg = f[keep], seg[keep]
+    sweep = b["point_sweep"][keep]
+    comp, _ = ops.propose_clusters(f.numpy(), 0.75)
+    comp = torch.from_numpy(comp)
+    cfg = R.edict(
+        ANGLE_REGULARIZER=10, COMPONENT_KEYS=["component_rad0x75"],
+        REGISTRATION=dict(GRAPH=dict(TYPE="RadiusGraph", RADIUS=[2.5, 1.25, 1.0], MAX_NUM_NEIGHBORS=1,
+                                     SORT_BY_DIST=True, RELATIVE_KEY="fxyz"),
+                          VOXEL_SIZE=[[0.4, 0.4, 0.6], [0.2, 0.2, 0.3], [0.1, 0.1, 0.15]],
+                          STOPPING_DELTA=[0.05, 0.05, 0.05]),
+        NN_GRAPH=dict(TYPE="RadiusGraph", RADIUS=0.5, MAX_NUM_NEIGHBORS=1, SORT_BY_DIST=True, RELATIVE_KEY="fxyz"),
+        DIR="/tmp/unused",
+        TRACKING_PARAMS=dict(REGISTRATION_ERROR_COEFFICIENT=0.13, TRACK_INTERVAL=8, ANGLE_THRESHOLD=45,
+                             MIN_MOVE_FRAME=6))
+    mod = ct.ClusterTracking(cfg, {})
+    seq_points = R.edict(fxyz=f.clone(), frame=sweep.clone(), gt_box_id=torch.zeros_like(comp) - 1,
+                         segmentation_label=seg.clone(), component=comp.clone())
+    diam = ct.component_diameter(seq_points)[seq_points.component]
+    seq_points.component_diameter = diam
+    seq_points.stationary = diam > 12.5
+    seq_points.extracted = torch.zeros_like(seq_points.fxyz[:, 0]).bool()
+    anchor = 8
+    frame_mask = (seq_points.fxyz[:, 0] == anchor).reshape(-1)
+    frame_points = R.edict(**cu.filter_dict(seq_points, frame_mask))
+    frame_points.component = frame_points.component - frame_points.component.min()
+    t0 = time.time()
+    torch.manual_seed(0)
+    ex = mod.track_frame(seq_points, frame_points, None)
+    print(f"reference track_frame took {time.time() - t0:.1f}s")
+    np.savez_compressed(os.path.join(OUT, "tracking.npz"), points=f.numpy(), sweep=sweep.numpy(), seg=seg.numpy(),
+                        component=comp.numpy(), anchor=np.array(anchor),
+                        ex_fxyz=ex.fxyz.numpy(), ex_component=ex.component.numpy(),
+                        ex_original_indices=ex.original_indices.numpy(), ex_frame_indices=ex.frame_indices.numpy(),
+                        ex_moving=ex.moving.numpy(), transforms=ex.transforms.numpy())
+    print("tracking.npz", f.shape, "extracted", ex.fxyz.shape, "components kept", ex.component.unique().numel(),
+          "transforms", tuple(ex.transforms.shape))

@@ -25,6 +25,16 @@ struct QueryRange {
   int nc;
 };
 
+// Up to three union-find forests fed by one search (multi-radius cluster proposals): forest k receives the list
+// entries with d2 <= r2[k]; a forest with need_full[k] set is only fed by queries whose list is full (cnt == K) --
+// for those the K nearest within the search radius are also the K nearest within any larger radius.
+struct UfTargets {
+  int *parent[3];
+  float r2[3];
+  int need_full[3];
+  int n;
+};
+
 constexpr int kWarpsPerBlock = 8;
 constexpr unsigned int kFull = 0xffffffffu;
 
@@ -44,7 +54,7 @@ radius_search_kernel(const pcs_slot_t *__restrict__ table, long long mask, const
                      const int *__restrict__ sorted_idx, SegGeom g, const float4 *__restrict__ queries,
                      long long m, const int *__restrict__ order, QueryRange qr, const float *__restrict__ radius,
                      float radius_scalar, int K, int *__restrict__ nbr_idx, float *__restrict__ nbr_d2,
-                     int *__restrict__ nbr_cnt, int *__restrict__ uf_parent) {
+                     int *__restrict__ nbr_cnt, UfTargets uf, const int *__restrict__ skip_full_cnt) {
   __shared__ float4 s_lo[PCS_MAX_SEGMENTS];
   __shared__ long long s_dims[PCS_MAX_SEGMENTS * 4];
   load_geom(g, s_lo, s_dims);
@@ -56,6 +66,8 @@ radius_search_kernel(const pcs_slot_t *__restrict__ table, long long mask, const
   for (long long w = (long long)blockIdx.x * kWarpsPerBlock + warp; w < m; w += nwarps) {
     // self-query mode (queries == NULL): the w-th row of the cell-sorted array queries its own grid
     const long long q = queries ? (order ? (long long)order[w] : w) : (long long)sorted_idx[w];
+    // second pass of the multi-radius search: queries whose finer-radius list was already full are done
+    if (skip_full_cnt && skip_full_cnt[q] >= K) continue;
     const float4 qp = queries ? queries[q] : sorted_pts[w];
     const float r = radius ? radius[q] : radius_scalar;
     const float r2 = __fmul_rn(r, r);
@@ -168,13 +180,19 @@ radius_search_kernel(const pcs_slot_t *__restrict__ table, long long mask, const
     if (nbr_d2 && lane < K) nbr_d2[q * K + lane] = lane < cnt ? __uint_as_float((unsigned int)(best >> 32)) : 0.f;
     if (nbr_cnt && lane == 0) nbr_cnt[q] = cnt;
     if (kFusedUF) {
-      // hook the roots of the query and of all its neighbours under the smallest of them
-      const int node = lane < cnt ? idx : (int)q;
-      const int root = uf_find(uf_parent, node);
-      const int rmin = (int)__reduce_min_sync(kFull, (unsigned int)root);
-      const unsigned int peers = __match_any_sync(kFull, root);
-      if (root != rmin && lane == __ffs(peers) - 1) uf_unite(uf_parent, root, rmin);
-      if (cnt == 32 && lane == 0) uf_unite(uf_parent, (int)q, rmin);
+      const float my_d2 = __uint_as_float((unsigned int)(best >> 32));
+      for (int k = 0; k < uf.n; k++) {
+        if (uf.need_full[k] && cnt < K) continue;
+        // hook the roots of the query and of its neighbours within r2[k] under the smallest of them
+        int *parent = uf.parent[k];
+        const bool use = lane < cnt && my_d2 <= uf.r2[k];
+        const int node = use ? idx : (int)q;
+        const int root = uf_find(parent, node);
+        const int rmin = (int)__reduce_min_sync(kFull, (unsigned int)root);
+        const unsigned int peers = __match_any_sync(kFull, root);
+        if (root != rmin && lane == __ffs(peers) - 1) uf_unite(parent, root, rmin);
+        if (lane == 0) uf_unite(parent, (int)q, rmin);
+      }
     }
   }
 }
@@ -211,11 +229,22 @@ int pcs_radius_search(pcs_stream_t s, const pcs_slot_t *table, int64_t H, const 
                       const int64_t *seg_dims, const float *vs, const float *queries, int64_t m,
                       const int32_t *order, const int *qmin, const int *qmax, const float *radius,
                       float radius_scalar, int K, int32_t *nbr_idx, float *nbr_d2, int32_t *nbr_cnt,
-                      int32_t *uf_parent) {
+                      int32_t *const *uf_parents, const float *uf_r2, const int *uf_need_full, int n_uf,
+                      const int32_t *skip_full_cnt) {
   if (!table || H < 2 || (H & (H - 1)) || K < 1 || K > PCS_MAX_K || n_seg < 1 || n_seg > PCS_MAX_SEGMENTS ||
       !qmin || !qmax || ((uintptr_t)queries & 15) || ((uintptr_t)sorted_pts & 15) || m < 0 || m >= (1LL << 31))
     return set_error(PCS_ERR_BAD_ARG, "pcs_radius_search: bad args (1 <= K <= 32, 16-byte aligned points)");
-  if (!uf_parent && !nbr_idx && !nbr_cnt) return set_error(PCS_ERR_BAD_ARG, "pcs_radius_search: no output requested");
+  if (n_uf < 0 || n_uf > 3 || (n_uf > 0 && (!uf_parents || !uf_r2 || !uf_need_full)))
+    return set_error(PCS_ERR_BAD_ARG, "pcs_radius_search: at most 3 union-find targets");
+  if (n_uf == 0 && !nbr_idx && !nbr_cnt) return set_error(PCS_ERR_BAD_ARG, "pcs_radius_search: no output requested");
+  UfTargets uf;
+  uf.n = n_uf;
+  for (int k = 0; k < 3; k++) {
+    uf.parent[k] = k < n_uf ? uf_parents[k] : nullptr;
+    uf.r2[k] = k < n_uf ? uf_r2[k] : 0.f;
+    uf.need_full[k] = k < n_uf ? uf_need_full[k] : 0;
+    if (k < n_uf && !uf.parent[k]) return set_error(PCS_ERR_BAD_ARG, "pcs_radius_search: null union-find forest");
+  }
   if (m == 0) return 0;
   QueryRange qr;
   qr.nc = 1;
@@ -229,14 +258,14 @@ int pcs_radius_search(pcs_stream_t s, const pcs_slot_t *table, int64_t H, const 
   long long blocks = (m + kWarpsPerBlock - 1) / kWarpsPerBlock;
   long long cap = 148LL * 8 * 4;  // a few waves of 8 resident CTAs per SM; warps stride over the queries
   int grid = (int)(blocks < cap ? blocks : cap);
-  if (uf_parent) {
+  if (n_uf > 0) {
     PCS_LAUNCH(radius_search_kernel<true>, grid, kWarpsPerBlock * 32, 0, as_stream(s), table, (long long)(H - 1),
                (const float4 *)sorted_pts, sorted_idx, g, (const float4 *)queries, (long long)m, order, qr, radius,
-               radius_scalar, K, nbr_idx, nbr_d2, nbr_cnt, uf_parent);
+               radius_scalar, K, nbr_idx, nbr_d2, nbr_cnt, uf, skip_full_cnt);
   } else {
     PCS_LAUNCH(radius_search_kernel<false>, grid, kWarpsPerBlock * 32, 0, as_stream(s), table, (long long)(H - 1),
                (const float4 *)sorted_pts, sorted_idx, g, (const float4 *)queries, (long long)m, order, qr, radius,
-               radius_scalar, K, nbr_idx, nbr_d2, nbr_cnt, uf_parent);
+               radius_scalar, K, nbr_idx, nbr_d2, nbr_cnt, uf, skip_full_cnt);
   }
   return 0;
 }

@@ -152,13 +152,14 @@ class CellGrid:
         return coords, keys
 
     def search(self, query, K, radius, qmin=(0, -1, -1, -1), qmax=(0, 1, 1, 1), order=None, want_d2=False,
-               uf_parent=None, want_lists=True):
+               uf_parent=None, want_lists=True, uf_targets=None, skip_full_cnt=None):
         """K nearest reference points within `radius` of every query (padded lists).
 
         query=None is the self-query mode: the grid's own points are the queries and are visited in
         cell order straight from the cell-sorted array (outputs are still indexed by original row).
-        radius: python float or float32 tensor [M].  Returns (nbr_idx i32[M,K] | None, nbr_cnt i32[M],
-        nbr_d2 f32[M,K] | None).
+        radius: python float or float32 tensor [M].  uf_parent: one union-find forest fed with every list entry;
+        uf_targets: list of up to 3 (forest, radius, need_full) for the multi-radius search.
+        Returns (nbr_idx i32[M,K] | None, nbr_cnt i32[M], nbr_d2 f32[M,K] | None).
         """
         if not (1 <= K <= PCS_MAX_K):
             raise _lib.PcsError(f"K must be in [1, {PCS_MAX_K}] (got {K})")
@@ -177,13 +178,21 @@ class CellGrid:
             rad_s = float(np.float32(radius))
         if order is not None:
             order = order.int().contiguous()
+        targets = list(uf_targets or [])
+        if uf_parent is not None:
+            targets = [(uf_parent, float("inf"), False)] + targets
+        n_uf = len(targets)
+        uf_ptrs = (ctypes.c_void_p * 3)(*[t[0].data_ptr() for t in targets] + [0] * (3 - n_uf))
+        uf_r2 = (ctypes.c_float * 3)(*[float(np.float32(t[1]) * np.float32(t[1])) if np.isfinite(t[1]) else 3.0e38
+                                       for t in targets] + [0.0] * (3 - n_uf))
+        uf_full = (ctypes.c_int * 3)(*[int(bool(t[2])) for t in targets] + [0] * (3 - n_uf))
         with torch.cuda.device(dev), _timed("radius_search", n_ref=self.n, n_query=m, K=int(K), lists=bool(want_lists),
-                                            fused_uf=uf_parent is not None):
+                                            fused_uf=n_uf):
             _lib.check(_lib.lib().pcs_radius_search(
                 _stream(), _ptr(self.table), self.H, _ptr(self.sorted_pts), _ptr(self.sorted_idx), self.seg_div,
                 self.n_seg, _ptr(self.seg_lo), _ptr(self.seg_dims), _f4(self.vs), _ptr(query), m, _ptr(order),
                 _i4(qmin), _i4(qmax), _ptr(rad_t), rad_s, int(K), _ptr(nbr_idx), _ptr(nbr_d2), _ptr(nbr_cnt),
-                _ptr(uf_parent)), "pcs_radius_search")
+                uf_ptrs, uf_r2, uf_full, n_uf, _ptr(skip_full_cnt)), "pcs_radius_search")
         return nbr_idx, nbr_cnt, nbr_d2
 
 
@@ -518,6 +527,40 @@ def register_icp(mov_fxyz, mov_comp, mov_stationary, ref_fxyz, ref_stationary, n
     T44[:, 3, 3] = 1.0
     ratio = match.float() / (comp_deg + 1e-6)  # :199
     return moved, T44, l1, ratio, istate
+
+
+def cluster_labels_multi(fxyz, radii, max_num_neighbors=32, chunk=10, num_frames=None):
+    """Multi-radius fused cluster proposals: ONE fine search serves every radius.
+
+    Pass A searches the finest radius on its own (reference-identical) grid.  A query whose list is full (K entries)
+    already holds its K nearest points overall, so the same list is united into the forests of all larger radii.
+    Pass B searches the coarsest radius only for the remaining (sparse-region) queries; intermediate radii take the
+    distance prefix of that list (top-K within r is the prefix of top-K within R >= r cut at d <= r).
+    Returns ([labels per radius, in the order of `radii`], [n_comp per radius]).
+    """
+    fxyz = _as_points(fxyz, "point_fxyz")
+    n = fxyz.shape[0]
+    K = int(max_num_neighbors)
+    if num_frames is None:
+        num_frames = int(fxyz[:, 0].max().item()) + 1
+    n_seg = max(1, (num_frames + chunk - 1) // chunk)
+    order = sorted(range(len(radii)), key=lambda i: radii[i])
+    r_sorted = [float(radii[i]) for i in order]
+    if len(r_sorted) < 2 or len(r_sorted) > 3:
+        raise _lib.PcsError("cluster_labels_multi expects 2 or 3 radii")
+    r_fine, r_coarse = r_sorted[0], r_sorted[-1]
+    parents = [uf_new(n, fxyz.device) for _ in r_sorted]
+    fine = CellGrid(fxyz, radius_voxel_size(r_fine), seg_div=chunk, n_seg=n_seg)
+    targets = [(parents[0], r_fine, False)] + [(p, float("inf"), True) for p in parents[1:]]
+    _, cnt_fine, _ = fine.search(None, K, r_fine, uf_targets=targets, want_lists=False)
+    coarse = CellGrid(fxyz, radius_voxel_size(r_coarse), seg_div=chunk, n_seg=n_seg)
+    targets = [(p, r, False) for p, r in zip(parents[1:], r_sorted[1:])]
+    coarse.search(None, K, r_coarse, uf_targets=targets, want_lists=False, skip_full_cnt=cnt_fine)
+    seg_of = point_segments(fxyz, chunk, n_seg)
+    labels, n_comp = [None] * len(radii), [None] * len(radii)
+    for pos, i in enumerate(order):
+        n_comp[i], labels[i] = uf_labels(parents[pos], seg_of, n_seg)
+    return labels, n_comp
 
 
 def launch_count():

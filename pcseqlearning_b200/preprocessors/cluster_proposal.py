@@ -33,6 +33,18 @@ class ClusterProposal(nn.Module):
         fxyz = seq_dict["point_fxyz"]
         num_frames = int(seq_dict["point_sweep"].max().long().item()) + 1
         verbose = self.model_cfg.get("VERBOSE", True)
+        graphs = [getattr(self, f"graph_{k}") for k in self.component_keys]
+        same_k = len({int(g.max_num_neighbors) for g in graphs}) == 1
+        if self.model_cfg.get("FUSE_RADII", True) and same_k and len(graphs) in (2, 3):
+            # multi-radius search: one fine search + one coarse search over the sparse remainder serve all radii
+            with Timer("Propose Cluster (multi-radius)", verbose=verbose):
+                labels, n_comp = ops.cluster_labels_multi(fxyz, [float(g.radius) for g in graphs],
+                                                          int(graphs[0].max_num_neighbors), chunk=CHUNK_FRAMES,
+                                                          num_frames=num_frames)
+            for comp_key, lab, nc in zip(self.component_keys, labels, n_comp):
+                seq_dict[f"point_{comp_key}"] = lab
+                seq_dict[f"num_{comp_key}"] = nc
+            return seq_dict
         for comp_key in self.component_keys:
             with Timer(f"Propose Cluster for {comp_key}", verbose=verbose):
                 graph = getattr(self, f"graph_{comp_key}")

@@ -169,3 +169,23 @@ def test_large_scale_properties():
     # labels: fused == edge route, endpoints of every edge share a label
     labels, _ = ops.cluster_labels(pts, r, K, chunk=10, num_frames=20)
     assert bool((labels[er] == labels[eq]).all())
+
+
+def test_multi_radius_fused_equals_separate_searches(golden_dir):
+    """The multi-radius search (one fine pass + one coarse pass over the sparse remainder) gives exactly the labels of
+    three independent searches, which equal the reference's."""
+    from pcseqlearning_b200 import ops
+    g = _load(golden_dir, "proposal.npz")
+    t = _cuda(g["points"])
+    labels, n_comp = ops.cluster_labels_multi(t, [1.25, 0.75, 0.25], 32, chunk=10)
+    for lab, key in zip(labels, ("component_rad1x25", "component_rad0x75", "component_rad0x25")):
+        np.testing.assert_array_equal(lab.cpu().numpy(), g[key])
+    # dense random cloud: most fine lists are full, so the coarse forests are fed by the fine pass
+    gen = torch.Generator(device="cuda").manual_seed(17)
+    n = 400_000
+    pts = torch.rand(n, 4, generator=gen, device="cuda") * torch.tensor([1.0, 40.0, 40.0, 3.0], device="cuda")
+    pts[:, 0] = torch.randint(0, 12, (n,), generator=gen, device="cuda").float()
+    labels, _ = ops.cluster_labels_multi(pts, [1.25, 0.75, 0.25], 32, chunk=10, num_frames=12)
+    for lab, r in zip(labels, (1.25, 0.75, 0.25)):
+        want, _ = ops.cluster_labels(pts, r, 32, chunk=10, num_frames=12)
+        assert torch.equal(lab, want), r
