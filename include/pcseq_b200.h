@@ -169,8 +169,8 @@ int pcs_group_median(pcs_stream_t s, const int64_t *values, const int64_t *inv, 
  * the global max|dw| < stopping_delta rule and the best-plane bookkeeping all run on the device.
  *   vox float4[Nv] (unused,x,y,z) sorted by super-pillar id cidx int32[Nv]; seg_start int32[C+1]
  *   origin float[C][3] local origins; cmin_z / cmax_z float[C]; ratios float[n_ratios]
- *   scratch (zero-filled by the caller): w float[Nv], acc double[3][C][10], nhit int32[3][C], gmax uint32[3],
- *   center / normal float[C][3]
+ *   scratch (zero-filled by the caller): acc double[3][R][C][10], nhit int32[3][R][C], gmax uint32[3][R],
+ *   planes float[2][R][C][6], fin int32[R][2]   (R = n_ratios <= 32; all ratios are iterated concurrently)
  *   outputs: best_center float[C][3] (init 0), best_normal float[C][3] (init (0,0,1)), best_conf float[C]
  *   (init 0), iters_out int32[n_ratios] (optional).
  * pcs_l1_heightfield replaces l1_minimization (preprocessor_utils.py:313-350): AdamW (torch defaults,
@@ -179,8 +179,8 @@ int pcs_group_median(pcs_stream_t s, const int64_t *values, const int64_t *inv, 
  * m / v zero-filled scratch, info int32[2] = (iterations run, stopped early), loss_out float[1]. */
 int pcs_ground_ransac(pcs_stream_t s, const float *vox, const int32_t *cidx, const int32_t *seg_start,
                       const float *origin, const float *cmin_z, const float *cmax_z, const float *ratios, int64_t Nv,
-                      int C, int n_ratios, float sigma2, float stopping_delta, int max_iter, float *w, double *acc,
-                      int32_t *nhit, uint32_t *gmax, float *center, float *normal, float *best_center,
+                      int C, int n_ratios, float sigma2, float stopping_delta, int max_iter, double *acc,
+                      int32_t *nhit, uint32_t *gmax, float *planes, int32_t *fin, float *best_center,
                       float *best_normal, float *best_conf, int32_t *iters_out);
 int pcs_l1_heightfield(pcs_stream_t s, const float *min_z, const float *weight, float *h, float *m, float *v, int X,
                        int Y, float lr, float lr_gamma, int decay_step, float rigid_weight, int max_iters,

@@ -49,7 +49,7 @@ _SIGNATURES = {
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pcs_ground_ransac": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_int64, c_int, c_int, c_float, c_float, c_int, c_void_p, c_void_p, c_void_p,
-                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pcs_l1_heightfield": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float,
                                    c_float, c_int, c_float, c_int, c_void_p, c_void_p]),
     "pcs_register_icp": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,

@@ -61,8 +61,14 @@ __device__ void smallest_eigvec3(const double a_in[6], float n_out[3]) {
 
 constexpr int kAcc = 10;         // S0, S1[3], S2[6]
 constexpr int kRansacThreads = 256;
-constexpr int kGroup = 128;      // super-pillars whose planes a block keeps in shared memory at a time
+constexpr int kGroup = 32;       // super-pillars whose planes a block keeps in shared memory at a time
+constexpr int kG = 3;            // height ratios processed together by one team of blocks
+constexpr int kMaxRatios = 32;
 
+// All height ratios of the reference's loop (preprocessor_utils.py:147-170) are independent IRLS problems that
+// differ only in their initial weights, so they are iterated CONCURRENTLY: one sweep over the voxels advances
+// every ratio by one IRLS iteration.  Nothing per (ratio, voxel) is stored: the previous weight needed by the
+// max|dw| stopping rule is recomputed from the previous plane, bit-identically.
 struct RansacArgs {
   const float4 *vox;       // [Nv] (unused, x, y, z) sorted by super-pillar
   const int *cidx;         // [Nv] super-pillar id (ascending)
@@ -70,33 +76,31 @@ struct RansacArgs {
   const float *origin;     // [C][3] local origin per super-pillar (any point near its voxels)
   const float *cmin_z;     // [C]
   const float *cmax_z;     // [C]
-  const float *ratios;     // [n_ratios]
-  float *w;                // [Nv] IRLS weights (scratch)
-  double *acc;             // [3][C][kAcc] rotating moment accumulators (zeroed by the caller)
-  int *nhit;               // [3][C] rotating hit counters (zeroed by the caller)
-  unsigned int *gmax;      // [3] max |dw| as float bits (zeroed by the caller)
-  float *center;           // [C][3] current plane centre (written by the pillar's owner block)
-  float *normal;           // [C][3] current plane normal
+  const float *ratios;     // [R]
+  double *acc;             // [3][R][C][kAcc] rotating moment accumulators (zeroed by the caller)
+  int *nhit;               // [3][R][C] rotating hit counters (zeroed by the caller)
+  unsigned int *gmax;      // [3][R] max |dw| as float bits (zeroed by the caller)
+  float *planes;           // [2][R][C][6] published planes (centre, normal) of the last two iterations
+  int *fin;                // [R][2] buffers holding the final planes / hit counts of every ratio
   float *best_center;      // [C][3] out
   float *best_normal;      // [C][3] out (initialised to (0,0,1) by the caller)
   float *best_conf;        // [C]    out (initialised to 0 by the caller)
-  int *iters_out;          // [n_ratios] IRLS iterations used per ratio (diagnostics)
+  int *iters_out;          // [R] IRLS iterations used per ratio
   long long Nv;
   int C;
-  int n_ratios;
+  int R;
   float sigma2;
   float stopping_delta;
   int max_iter;
 };
 
-struct Plane {
-  float cx, cy, cz, nx, ny, nz, ox, oy, oz;
+struct PlaneN {  // plane being evaluated: centre, normal
+  float cx, cy, cz, nx, ny, nz;
 };
 
-// plane of super-pillar p from the accumulated moments: centre = (sum w x)/(sum w + 1e-6), normal = eigenvector of
-// the smallest eigenvalue of mean_i w_i d_i d_i^T (preprocessor_utils.py:47-71); moments are relative to origin[p]
-__device__ __noinline__ void fit_plane(const RansacArgs &A, int p, const double *acc_buf, Plane &pl) {
-  const double *s = acc_buf + (long long)p * kAcc;
+// plane of super-pillar p from accumulated moments: centre = (sum w x)/(sum w + 1e-6), normal = eigenvector of the
+// smallest eigenvalue of mean_i w_i d_i d_i^T (preprocessor_utils.py:47-71); moments are relative to origin[p]
+__device__ __noinline__ void fit_plane(const RansacArgs &A, int p, const double *s, PlaneN &pl) {
   const double S0 = s[0];
   const double ox = A.origin[p * 3 + 0], oy = A.origin[p * 3 + 1], oz = A.origin[p * 3 + 2];
   const double inv = 1.0 / (S0 + 1e-6);
@@ -119,148 +123,188 @@ __device__ __noinline__ void fit_plane(const RansacArgs &A, int p, const double 
   pl.nx = nrm[0];
   pl.ny = nrm[1];
   pl.nz = nrm[2];
-  pl.ox = (float)ox;
-  pl.oy = (float)oy;
-  pl.oz = (float)oz;
 }
 
-__device__ __forceinline__ void warp_flush(float *acc10, int &hits, int pid, double *acc_buf, int *nhit_buf, int lane) {
+// IRLS weight of a voxel for a plane (preprocessor_utils.py:72-75); err returned for the hit test.
+// One fast reciprocal for both factors: sigma2 * 0.25 / ((err^2 + sigma2) (|d|^2 + 0.25)); the weights feed a
+// tolerance-compared fit, and the previous weight is recomputed with the same expression (bit-identical).
+__device__ __forceinline__ float plane_weight(const PlaneN &pl, float x, float y, float z, float sigma2, float &err) {
+  const float dx = x - pl.cx, dy = y - pl.cy, dz = z - pl.cz;
+  err = fabsf(dx * pl.nx + dy * pl.ny + dz * pl.nz);
+  const float den = (err * err + sigma2) * (dx * dx + dy * dy + dz * dz + 0.25f);
+  return __fdividef(sigma2 * 0.25f, den);
+}
+
+__device__ __forceinline__ float prior_weight(float prior_z, float z, float sigma2) {
+  const float zd = prior_z - z;
+  return __fdividef(sigma2, zd * zd + sigma2);
+}
+
+__device__ __forceinline__ void warp_flush(float *acc10, int &hits, double *dst, int *hit_dst, int lane) {
 #pragma unroll
   for (int k = 0; k < kAcc; k++) {
     double v = (double)acc10[k];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if (lane == 0 && v != 0.0) atomicAdd(acc_buf + (long long)pid * kAcc + k, v);
+    if (lane == 0 && v != 0.0) atomicAdd(dst + k, v);
     acc10[k] = 0.f;
   }
   int h = hits;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) h += __shfl_down_sync(0xffffffffu, h, o);
-  if (lane == 0 && h != 0) atomicAdd(nhit_buf + pid, h);
+  if (lane == 0 && h != 0) atomicAdd(hit_dst, h);
   hits = 0;
 }
 
-// One IRLS half-step of a block over its contiguous voxel range [v0, v1):
-//   fit the planes of the super-pillars in the range from acc_fit (skipped when `first`: weights come from
-//   the height prior), evaluate them on every voxel (new weight, |dw|, hit) and accumulate the moments of the
-//   NEXT fit into acc_next.  Pillars are handled in groups of kGroup whose planes live in shared memory.
-//   The block that owns a pillar (holds its first voxel) publishes the plane and clears the spare buffers.
-__device__ void ransac_step(const RansacArgs &A, long long v0, long long v1, bool first, float ratio,
-                            const double *acc_fit, double *acc_next, int *nhit_next, unsigned int *gmax_next,
-                            double *acc_spare, int *nhit_spare, Plane *s_plane) {
+// One IRLS iteration of a team (ratios [r0, r0+nr)) over the block's contiguous voxel range [v0, v1).
+//   it < 0  : weights from the height prior, moments of fit 0
+//   it >= 0 : fit plane `it` from acc[bf]; previous plane = prior (it == 0) or planes[(it-1)&1]; evaluate the new
+//             plane (weight, |dw|, hit) and accumulate the moments of fit it+1 into acc[bn].
+// The block that owns a pillar (holds its first voxel) publishes its planes and clears the spare buffers.
+__device__ void ransac_step(const RansacArgs &A, long long v0, long long v1, int it, int r0, int nr, unsigned int done,
+                            float (*s_new)[kGroup][8], float (*s_old)[kGroup][8], float (*s_org)[3]) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nwarp = kRansacThreads / 32;
   const float sigma = sqrtf(A.sigma2);
-  float dmax = 0.f;
+  const long long RC = (long long)A.R * A.C;
+  const int bf = ((it % 3) + 3) % 3, bn = (it + 1) % 3, bs = (it + 2) % 3;
+  const bool first = it < 0;
+  double *acc_fit = A.acc + (long long)bf * RC * kAcc;
+  double *acc_next = A.acc + (long long)(first ? 0 : bn) * RC * kAcc;
+  double *acc_spare = A.acc + (long long)(first ? 2 : bs) * RC * kAcc;
+  int *nhit_next = A.nhit + (long long)(first ? 0 : bn) * RC;
+  int *nhit_spare = A.nhit + (long long)(first ? 2 : bs) * RC;
+  unsigned int *gmax_next = A.gmax + (first ? 0 : bn) * A.R;
+  float *pub_new = A.planes + (long long)(it & 1) * RC * 6;
+  const float *pub_old = A.planes + (long long)((it - 1) & 1) * RC * 6;
+  float dmax[kG];
+#pragma unroll
+  for (int g = 0; g < kG; g++) dmax[g] = 0.f;
   if (v1 > v0) {
     const int p_first = A.cidx[v0], p_last = A.cidx[v1 - 1];
     for (int g0 = p_first; g0 <= p_last; g0 += kGroup) {
       const int g1 = min(g0 + kGroup, p_last + 1);  // pillars [g0, g1)
       __syncthreads();
-      for (int p = g0 + threadIdx.x; p < g1; p += kRansacThreads) {
-        Plane pl;
-        if (!first) {
-          fit_plane(A, p, acc_fit, pl);
-        } else {
-          pl.ox = A.origin[p * 3 + 0];
-          pl.oy = A.origin[p * 3 + 1];
-          pl.oz = A.origin[p * 3 + 2];
-          pl.cx = A.cmin_z[p] * ratio + A.cmax_z[p] * (1.0f - ratio);  // prior height (preprocessor_utils.py:148)
-          pl.cy = pl.cz = pl.nx = pl.ny = pl.nz = 0.f;
+      for (int t = threadIdx.x; t < (g1 - g0) * nr; t += kRansacThreads) {
+        const int p = g0 + t / nr, g = t % nr, r = r0 + g;
+        const long long rp = (long long)r * A.C + p;
+        if (g == 0) {
+          s_org[p - g0][0] = A.origin[p * 3 + 0];
+          s_org[p - g0][1] = A.origin[p * 3 + 1];
+          s_org[p - g0][2] = A.origin[p * 3 + 2];
         }
-        s_plane[p - g0] = pl;
+        if ((done >> r) & 1u) continue;
         const long long ps = A.seg_start[p];
-        if (ps >= v0 && ps < v1 && A.seg_start[p + 1] > ps) {  // owner of a non-empty pillar
-          if (!first) {
-            A.center[p * 3 + 0] = pl.cx;
-            A.center[p * 3 + 1] = pl.cy;
-            A.center[p * 3 + 2] = pl.cz;
-            A.normal[p * 3 + 0] = pl.nx;
-            A.normal[p * 3 + 1] = pl.ny;
-            A.normal[p * 3 + 2] = pl.nz;
+        const bool owner = ps >= v0 && ps < v1 && A.seg_start[p + 1] > ps;
+        if (first) {
+          // "plane" of the prior: only its height is used
+          s_new[g][p - g0][0] = A.cmin_z[p] * A.ratios[r] + A.cmax_z[p] * (1.0f - A.ratios[r]);  // :148
+        } else {
+          PlaneN pl;
+          fit_plane(A, p, acc_fit + rp * kAcc, pl);
+          float *d = s_new[g][p - g0];
+          d[0] = pl.cx; d[1] = pl.cy; d[2] = pl.cz; d[3] = pl.nx; d[4] = pl.ny; d[5] = pl.nz;
+          float *o = s_old[g][p - g0];
+          if (it == 0) {
+            o[0] = A.cmin_z[p] * A.ratios[r] + A.cmax_z[p] * (1.0f - A.ratios[r]);
+          } else {
+            for (int k = 0; k < 6; k++) o[k] = pub_old[rp * 6 + k];
           }
-          for (int k = 0; k < kAcc; k++) acc_spare[(long long)p * kAcc + k] = 0.0;
-          nhit_spare[p] = 0;
+          if (owner)
+            for (int k = 0; k < 6; k++) pub_new[rp * 6 + k] = d[k];
+        }
+        if (owner) {
+          for (int k = 0; k < kAcc; k++) acc_spare[rp * kAcc + k] = 0.0;
+          nhit_spare[rp] = 0;
         }
       }
       __syncthreads();
-      // voxels of this pillar group inside the block's range
       const long long a = max(v0, (long long)A.seg_start[g0]);
       const long long b = min(v1, (long long)A.seg_start[g1]);
-      float acc[kAcc];
+      float acc[kG][kAcc];
+      int hits[kG];
 #pragma unroll
-      for (int k = 0; k < kAcc; k++) acc[k] = 0.f;
-      int hits = 0;
+      for (int g = 0; g < kG; g++) {
+        hits[g] = 0;
+#pragma unroll
+        for (int k = 0; k < kAcc; k++) acc[g][k] = 0.f;
+      }
       int cur = -1;
-      constexpr int U = 4;  // warp steps whose loads are issued together (memory-level parallelism)
-      for (long long base0 = a + warp * 32; base0 < b; base0 += (long long)U * nwarp * 32) {
-        int pidv[U];
-        float4 pv[U];
-        float wold[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-          const long long i = base0 + (long long)u * nwarp * 32 + lane;
-          pidv[u] = -1;
-          if (i < b) {
-            pidv[u] = __ldg(A.cidx + i);
-            pv[u] = __ldg(A.vox + i);
-            wold[u] = first ? 0.f : A.w[i];
-          }
+      for (long long base = a + warp * 32; base < b; base += nwarp * 32) {
+        const long long i = base + lane;
+        const bool valid = i < b;
+        int pid = -1;
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) {
+          pid = __ldg(A.cidx + i);
+          p = __ldg(A.vox + i);
         }
+        const int pl0 = __shfl_sync(0xffffffffu, pid, 0);
+        const bool uniform = __all_sync(0xffffffffu, (!valid) || pid == pl0) && pl0 >= 0;
+        if (uniform && pl0 != cur) {
+          if (cur >= 0) {
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-          const long long i = base0 + (long long)u * nwarp * 32 + lane;
-          const int pid = pidv[u];
-          const bool valid = pid >= 0;
-          float wnew = 0.f, xr = 0.f, yr = 0.f, zr = 0.f;
-          int hit = 0;
-          if (valid) {
-            const float4 p = pv[u];
-            const Plane &pl = s_plane[pid - g0];
-            if (first) {
-              const float zd = pl.cx - p.w;
-              wnew = A.sigma2 / (zd * zd + A.sigma2);
-            } else {
-              const float dx = p.y - pl.cx, dy = p.z - pl.cy, dz = p.w - pl.cz;
-              const float err = fabsf(dx * pl.nx + dy * pl.ny + dz * pl.nz);
-              hit = err < sigma;
-              const float nw = A.sigma2 / (err * err + A.sigma2);
-              const float dw = 0.25f / (dx * dx + dy * dy + dz * dz + 0.25f);
-              wnew = nw * dw;
-              dmax = fmaxf(dmax, fabsf(wnew - wold[u]));
-            }
-            A.w[i] = wnew;
-            xr = p.y - pl.ox;
-            yr = p.z - pl.oy;
-            zr = p.w - pl.oz;
+            for (int g = 0; g < kG; g++)
+              if (g < nr && !((done >> (r0 + g)) & 1u))
+                warp_flush(acc[g], hits[g], acc_next + ((long long)(r0 + g) * A.C + cur) * kAcc,
+                           nhit_next + (long long)(r0 + g) * A.C + cur, lane);
           }
-          const int pl0 = __shfl_sync(0xffffffffu, pid, 0);
-          const bool uniform = __all_sync(0xffffffffu, (!valid) || pid == pl0) && pl0 >= 0;
-          if (uniform) {
-            if (pl0 != cur) {
-              if (cur >= 0) warp_flush(acc, hits, cur, acc_next, nhit_next, lane);
-              cur = pl0;
+          cur = pl0;
+        }
+        if (!uniform && cur >= 0) {
+#pragma unroll
+          for (int g = 0; g < kG; g++)
+            if (g < nr && !((done >> (r0 + g)) & 1u))
+              warp_flush(acc[g], hits[g], acc_next + ((long long)(r0 + g) * A.C + cur) * kAcc,
+                         nhit_next + (long long)(r0 + g) * A.C + cur, lane);
+          cur = -1;
+        }
+        if (valid) {
+          const int lp = pid - g0;
+          const float xr = p.y - s_org[lp][0], yr = p.z - s_org[lp][1], zr = p.w - s_org[lp][2];
+#pragma unroll
+          for (int g = 0; g < kG; g++) {
+            if (g >= nr || ((done >> (r0 + g)) & 1u)) continue;
+            float wnew;
+            int hit = 0;
+            if (first) {
+              wnew = prior_weight(s_new[g][lp][0], p.w, A.sigma2);
+            } else {
+              const float4 na = *reinterpret_cast<const float4 *>(s_new[g][lp]);
+              const float2 nb = *reinterpret_cast<const float2 *>(s_new[g][lp] + 4);
+              const PlaneN pn = {na.x, na.y, na.z, na.w, nb.x, nb.y};
+              float err;
+              wnew = plane_weight(pn, p.y, p.z, p.w, A.sigma2, err);
+              hit = err < sigma;
+              float wold;
+              const float *o = s_old[g][lp];
+              if (it == 0) {
+                wold = prior_weight(o[0], p.w, A.sigma2);
+              } else {
+                const float4 oa = *reinterpret_cast<const float4 *>(o);
+                const float2 ob = *reinterpret_cast<const float2 *>(o + 4);
+                const PlaneN po = {oa.x, oa.y, oa.z, oa.w, ob.x, ob.y};
+                float e2;
+                wold = plane_weight(po, p.y, p.z, p.w, A.sigma2, e2);
+              }
+              dmax[g] = fmaxf(dmax[g], fabsf(wnew - wold));
             }
-            if (valid) {
+            if (uniform) {
               const float wx = wnew * xr, wy = wnew * yr, wz = wnew * zr;
-              acc[0] += wnew;
-              acc[1] += wx;
-              acc[2] += wy;
-              acc[3] += wz;
-              acc[4] += wx * xr;
-              acc[5] += wx * yr;
-              acc[6] += wx * zr;
-              acc[7] += wy * yr;
-              acc[8] += wy * zr;
-              acc[9] += wz * zr;
-              hits += hit;
-            }
-          } else if (__any_sync(0xffffffffu, valid)) {
-            if (cur >= 0) warp_flush(acc, hits, cur, acc_next, nhit_next, lane);
-            cur = -1;
-            if (valid) {  // a pillar boundary inside this warp step: per-lane atomics
+              acc[g][0] += wnew;
+              acc[g][1] += wx;
+              acc[g][2] += wy;
+              acc[g][3] += wz;
+              acc[g][4] += wx * xr;
+              acc[g][5] += wx * yr;
+              acc[g][6] += wx * zr;
+              acc[g][7] += wy * yr;
+              acc[g][8] += wy * zr;
+              acc[g][9] += wz * zr;
+              hits[g] += hit;
+            } else {  // a pillar boundary inside this warp step: per-lane atomics
               const double w = wnew, x = xr, y = yr, z = zr;
-              double *d = acc_next + (long long)pid * kAcc;
+              double *d = acc_next + ((long long)(r0 + g) * A.C + pid) * kAcc;
               atomicAdd(d + 0, w);
               atomicAdd(d + 1, w * x);
               atomicAdd(d + 2, w * y);
@@ -271,67 +315,91 @@ __device__ void ransac_step(const RansacArgs &A, long long v0, long long v1, boo
               atomicAdd(d + 7, w * y * y);
               atomicAdd(d + 8, w * y * z);
               atomicAdd(d + 9, w * z * z);
-              if (hit) atomicAdd(nhit_next + pid, 1);
+              if (hit) atomicAdd(nhit_next + (long long)(r0 + g) * A.C + pid, 1);
             }
           }
         }
       }
-      if (cur >= 0) warp_flush(acc, hits, cur, acc_next, nhit_next, lane);
+      if (cur >= 0) {
+#pragma unroll
+        for (int g = 0; g < kG; g++)
+          if (g < nr && !((done >> (r0 + g)) & 1u))
+            warp_flush(acc[g], hits[g], acc_next + ((long long)(r0 + g) * A.C + cur) * kAcc,
+                       nhit_next + (long long)(r0 + g) * A.C + cur, lane);
+      }
     }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) dmax = fmaxf(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
-  if (lane == 0 && dmax > 0.f) atomicMax(gmax_next, __float_as_uint(dmax));
+  for (int g = 0; g < kG; g++) {
+    float d = dmax[g];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d = fmaxf(d, __shfl_xor_sync(0xffffffffu, d, o));
+    if (lane == 0 && d > 0.f && g < nr) atomicMax(gmax_next + r0 + g, __float_as_uint(d));
+  }
 }
 
 __global__ void __launch_bounds__(kRansacThreads, 3) ground_ransac_kernel(RansacArgs A) {
   cg::grid_group grid = cg::this_grid();
-  __shared__ Plane s_plane[kGroup];
-  // contiguous, 32-aligned voxel range of this block
-  const long long per = (((A.Nv + gridDim.x - 1) / gridDim.x) + 31) / 32 * 32;
-  const long long v0 = min((long long)blockIdx.x * per, A.Nv), v1 = min(v0 + per, A.Nv);
-  const long long accN = (long long)A.C * kAcc;
-  for (int r = 0; r < A.n_ratios; r++) {
-    const float ratio = A.ratios[r];
-    // weights from the height prior; moments of fit 0 -> buffer 0 (buffers 1 and 2 are clear)
-    ransac_step(A, v0, v1, true, ratio, nullptr, A.acc, A.nhit, A.gmax + 0, A.acc + 2 * accN, A.nhit + 2 * A.C, s_plane);
+  __shared__ __align__(16) float s_new[kG][kGroup][8];
+  __shared__ __align__(16) float s_old[kG][kGroup][8];
+  __shared__ float s_org[kGroup][3];
+  // teams of blocks: team t iterates ratios [t*kG, t*kG + kG); inside a team every block owns a contiguous,
+  // 32-aligned voxel range
+  const int n_teams = (A.R + kG - 1) / kG;
+  const int bpt = gridDim.x / n_teams;  // blocks per team (grid is a multiple of n_teams)
+  const int team = blockIdx.x / bpt, brank = blockIdx.x % bpt;
+  const int r0 = team * kG, nr = min(kG, A.R - r0);
+  const long long per = (((A.Nv + bpt - 1) / bpt) + 31) / 32 * 32;
+  const long long v0 = min((long long)brank * per, A.Nv), v1 = min(v0 + per, A.Nv);
+  const unsigned int all_done = (A.R >= 32) ? 0xffffffffu : ((1u << A.R) - 1u);
+  unsigned int done = 0;
+
+  ransac_step(A, v0, v1, -1, r0, nr, done, s_new, s_old, s_org);
+  grid.sync();
+  int it = 0;
+  for (; it < A.max_iter && done != all_done; it++) {
+    const int bn = (it + 1) % 3, bs = (it + 2) % 3;
+    if (blockIdx.x == 0)
+      for (int r = threadIdx.x; r < A.R; r += kRansacThreads) A.gmax[bs * A.R + r] = 0u;
+    ransac_step(A, v0, v1, it, r0, nr, done, s_new, s_old, s_org);
     grid.sync();
-    int it = 0, last_eval = 0;
-    for (; it < A.max_iter; it++) {
-      const int bf = it % 3, bn = (it + 1) % 3, bs = (it + 2) % 3;
-      if (blockIdx.x == 0 && threadIdx.x == 0) A.gmax[bs] = 0u;
-      ransac_step(A, v0, v1, false, ratio, A.acc + bf * accN, A.acc + bn * accN, A.nhit + bn * A.C, A.gmax + bn,
-                  A.acc + bs * accN, A.nhit + bs * A.C, s_plane);
-      last_eval = bn;
-      grid.sync();
-      if (__uint_as_float(A.gmax[bn]) < A.stopping_delta) {
-        ++it;
-        break;
+    // per-ratio stopping rule (preprocessor_utils.py:76-78), evaluated identically by every thread
+    for (int r = 0; r < A.R; r++) {
+      if ((done >> r) & 1u) continue;
+      const bool conv = __uint_as_float(A.gmax[bn * A.R + r]) < A.stopping_delta;
+      if (conv || it + 1 == A.max_iter) {
+        done |= 1u << r;
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+          A.fin[r * 2 + 0] = it & 1;  // planes buffer of the last fit
+          A.fin[r * 2 + 1] = bn;      // hit counters of the last evaluation
+          A.iters_out[r] = it + 1;
+        }
       }
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0 && A.iters_out) A.iters_out[r] = it;
-    // owners keep the plane that explains the most voxels (preprocessor_utils.py:160-170) and clear all buffers
-    if (v1 > v0) {
-      const int p_first = A.cidx[v0], p_last = A.cidx[v1 - 1];
-      for (int p = p_first + threadIdx.x; p <= p_last; p += kRansacThreads) {
-        const long long ps = A.seg_start[p];
-        if (!(ps >= v0 && ps < v1 && A.seg_start[p + 1] > ps)) continue;
-        const float nh = (float)A.nhit[last_eval * A.C + p];
-        if (A.best_conf[p] < nh) {
-          A.best_conf[p] = nh;
+  }
+  grid.sync();
+  // owners (team 0) keep, ratio after ratio, the plane that explains the most voxels (:160-170)
+  if (team == 0 && v1 > v0) {
+    const long long RC = (long long)A.R * A.C;
+    const int p_first = A.cidx[v0], p_last = A.cidx[v1 - 1];
+    for (int p = p_first + threadIdx.x; p <= p_last; p += kRansacThreads) {
+      const long long ps = A.seg_start[p];
+      if (!(ps >= v0 && ps < v1 && A.seg_start[p + 1] > ps)) continue;
+      float bc = A.best_conf[p];
+      for (int r = 0; r < A.R; r++) {
+        const long long rp = (long long)r * A.C + p;
+        const float nh = (float)A.nhit[(long long)A.fin[r * 2 + 1] * RC + rp];
+        if (bc < nh) {
+          bc = nh;
+          const float *pl = A.planes + ((long long)A.fin[r * 2 + 0] * RC + rp) * 6;
           for (int k = 0; k < 3; k++) {
-            A.best_normal[p * 3 + k] = A.normal[p * 3 + k];
-            A.best_center[p * 3 + k] = A.center[p * 3 + k];
+            A.best_center[p * 3 + k] = pl[k];
+            A.best_normal[p * 3 + k] = pl[3 + k];
           }
         }
-        for (int bsel = 0; bsel < 3; bsel++) {
-          for (int k = 0; k < kAcc; k++) A.acc[bsel * accN + (long long)p * kAcc + k] = 0.0;
-          A.nhit[bsel * A.C + p] = 0;
-        }
       }
+      A.best_conf[p] = bc;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) A.gmax[0] = A.gmax[1] = A.gmax[2] = 0u;
-    grid.sync();
   }
 }
 
@@ -511,11 +579,12 @@ extern "C" {
 
 int pcs_ground_ransac(pcs_stream_t s, const float *vox, const int32_t *cidx, const int32_t *seg_start,
                       const float *origin, const float *cmin_z, const float *cmax_z, const float *ratios, int64_t Nv,
-                      int C, int n_ratios, float sigma2, float stopping_delta, int max_iter, float *w, double *acc,
-                      int32_t *nhit, uint32_t *gmax, float *center, float *normal, float *best_center,
+                      int C, int n_ratios, float sigma2, float stopping_delta, int max_iter, double *acc,
+                      int32_t *nhit, uint32_t *gmax, float *planes, int32_t *fin, float *best_center,
                       float *best_normal, float *best_conf, int32_t *iters_out) {
-  if (Nv < 0 || C < 1 || n_ratios < 1 || ((uintptr_t)vox & 15) || !cidx || !seg_start || !acc || !nhit || !gmax)
-    return set_error(PCS_ERR_BAD_ARG, "pcs_ground_ransac: bad args");
+  if (Nv < 0 || C < 1 || n_ratios < 1 || n_ratios > kMaxRatios || ((uintptr_t)vox & 15) || !cidx || !seg_start ||
+      !acc || !nhit || !gmax || !planes || !fin || !iters_out)
+    return set_error(PCS_ERR_BAD_ARG, "pcs_ground_ransac: bad args (1 <= n_ratios <= 32)");
   RansacArgs A;
   A.vox = (const float4 *)vox;
   A.cidx = cidx;
@@ -524,19 +593,18 @@ int pcs_ground_ransac(pcs_stream_t s, const float *vox, const int32_t *cidx, con
   A.cmin_z = cmin_z;
   A.cmax_z = cmax_z;
   A.ratios = ratios;
-  A.w = w;
   A.acc = acc;
   A.nhit = nhit;
   A.gmax = gmax;
-  A.center = center;
-  A.normal = normal;
+  A.planes = planes;
+  A.fin = fin;
   A.best_center = best_center;
   A.best_normal = best_normal;
   A.best_conf = best_conf;
   A.iters_out = iters_out;
   A.Nv = Nv;
   A.C = C;
-  A.n_ratios = n_ratios;
+  A.R = n_ratios;
   A.sigma2 = sigma2;
   A.stopping_delta = stopping_delta;
   A.max_iter = max_iter;
@@ -545,11 +613,13 @@ int pcs_ground_ransac(pcs_stream_t s, const float *vox, const int32_t *cidx, con
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ground_ransac_kernel, kRansacThreads, 0);
   if (per_sm < 1) per_sm = 1;
-  if (per_sm > 4) per_sm = 4;
-  long long blocks = (Nv + 2047) / 2048;  // at least ~2k voxels per block
-  long long cap = (long long)sms * per_sm;
-  if (blocks > cap) blocks = cap;
-  if (blocks < 1) blocks = 1;
+  if (per_sm > 3) per_sm = 3;
+  const int n_teams = (n_ratios + kG - 1) / kG;
+  long long bpt = (Nv + 4095) / 4096;  // at least ~4k voxels per block
+  long long cap = ((long long)sms * per_sm) / n_teams;
+  if (bpt > cap) bpt = cap;
+  if (bpt < 1) bpt = 1;
+  long long blocks = bpt * n_teams;
   void *args[] = {&A};
   cudaError_t e = cudaLaunchCooperativeKernel((void *)ground_ransac_kernel, dim3((unsigned)blocks),
                                               dim3(kRansacThreads), args, 0, as_stream(s));

@@ -416,12 +416,12 @@ def ground_ransac(vox_sorted, cidx_sorted, num_coarse, cmin_z, cmax_z, ratios, s
     first = seg_start[:-1].long().clamp(max=max(Nv - 1, 0))
     origin = torch.where((counts > 0)[:, None], vox[first, 1:], torch.zeros(C, 3, device=dev)).contiguous()
     ratios = ratios.float().contiguous().to(dev)
-    w = torch.zeros(max(Nv, 1), dtype=torch.float32, device=dev)
-    acc = torch.zeros(3 * C * 10, dtype=torch.float64, device=dev)
-    nhit = torch.zeros(3 * C, dtype=torch.int32, device=dev)
-    gmax = torch.zeros(4, dtype=torch.int32, device=dev)
-    center = torch.zeros(C, 3, dtype=torch.float32, device=dev)
-    normal = torch.zeros(C, 3, dtype=torch.float32, device=dev)
+    R = int(ratios.shape[0])
+    acc = torch.zeros(3 * R * C * 10, dtype=torch.float64, device=dev)
+    nhit = torch.zeros(3 * R * C, dtype=torch.int32, device=dev)
+    gmax = torch.zeros(3 * R, dtype=torch.int32, device=dev)
+    planes = torch.zeros(2 * R * C * 6, dtype=torch.float32, device=dev)
+    fin = torch.zeros(R * 2, dtype=torch.int32, device=dev)
     best_center = torch.zeros(C, 3, dtype=torch.float32, device=dev)
     best_normal = torch.zeros(C, 3, dtype=torch.float32, device=dev)
     best_normal[:, 2] = 1.0
@@ -431,8 +431,8 @@ def ground_ransac(vox_sorted, cidx_sorted, num_coarse, cmin_z, cmax_z, ratios, s
         _lib.check(_lib.lib().pcs_ground_ransac(
             _stream(), _ptr(vox), _ptr(cidx), _ptr(seg_start), _ptr(origin), _ptr(cmin_z.float().contiguous()),
             _ptr(cmax_z.float().contiguous()), _ptr(ratios), Nv, C, int(ratios.shape[0]), float(sigma2),
-            float(stopping_delta), int(max_iter), _ptr(w), _ptr(acc), _ptr(nhit), _ptr(gmax), _ptr(center),
-            _ptr(normal), _ptr(best_center), _ptr(best_normal), _ptr(best_conf), _ptr(iters)), "pcs_ground_ransac")
+            float(stopping_delta), int(max_iter), _ptr(acc), _ptr(nhit), _ptr(gmax), _ptr(planes), _ptr(fin),
+            _ptr(best_center), _ptr(best_normal), _ptr(best_conf), _ptr(iters)), "pcs_ground_ransac")
     return best_center, best_normal, best_conf, iters
 
 
