@@ -34,6 +34,17 @@ WORKLOAD = "ground removal + 0.08m voxelization + multi-radius graph + CC propos
 POINT_KEYS = ["point_bxyz", "point_sweep", "point_feat", "segmentation_label", "instance_label"]
 
 
+def measured_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("radius_search_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -199,7 +210,7 @@ def run_ours(args, rank, world, local_rank):
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "radius_search_kernel<fused union-find>", "achieved": round(achieved, 2),
                      "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": round(achieved / peak, 5),
-                     "traffic": None, "launches_timed": len(durs), "mean_launch_ms": round(mean_ms, 4),
+                     "traffic": measured_traffic(), "launches_timed": len(durs), "mean_launch_ms": round(mean_ms, 4),
                      "algorithmic_bytes_per_launch": alg_bytes,
                      "hash_build": {"achieved": round(hb_n * 28 / (hb_ms * 1e-3) / 1e9, 2) if hb else None,
                                     "mean_ms": round(hb_ms, 4), "algorithmic_bytes_per_launch": hb_n * 28}},
