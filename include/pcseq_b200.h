@@ -210,6 +210,12 @@ int pcs_register_icp(pcs_stream_t s, const float *geo_lo, const float *geo_vs, c
                      double *mom, double *Ti, double *T, double *mu, double *l1_sum, double *state, int32_t *istate,
                      double *l1_err, int32_t *match_cnt);
 
+/* Curvature pruning of plane centres ("Truncated Least Squares", preprocessor_utils.py:175-193): for every threshold
+ * (descending), kNN (self included) mean curvature of the surviving planes; planes with curvature >= threshold are
+ * dropped whenever threshold <= max curvature.  One persistent CTA.  xyz / normal float[n][3], keep int32[n] out. */
+int pcs_plane_prune(pcs_stream_t s, const float *xyz, const float *normal, int n, int K, const float *thresholds,
+                    int n_thr, int32_t *keep);
+
 #ifdef __cplusplus
 }
 #endif

@@ -258,11 +258,16 @@ __global__ void __launch_bounds__(256) hash_scatter_kernel(const float4 *__restr
     int base = 0;
     if (valid && lane == leader) {
       long long slot = hash_key(key) & mask;
-      while (*((volatile long long *)&table[slot].key) != key) slot = (slot + 1) & mask;
-      base = atomicAdd(&table[slot].start, __popc(peers));
+      long long probes = 0;
+      // bounded: a key that could not be inserted (table overflow, flagged in counters[2]) is simply not found
+      while (*((volatile long long *)&table[slot].key) != key && probes <= mask) {
+        slot = (slot + 1) & mask;
+        ++probes;
+      }
+      base = (probes <= mask) ? atomicAdd(&table[slot].start, __popc(peers)) : -1;
     }
     base = __shfl_sync(0xffffffffu, base, leader);
-    if (valid) {
+    if (valid && base >= 0) {
       int pos = base + __popc(peers & ((1u << lane) - 1));
       sorted_pts[pos] = p;
       sorted_idx[pos] = (int)i;

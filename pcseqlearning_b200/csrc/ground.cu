@@ -661,3 +661,121 @@ int pcs_l1_heightfield(pcs_stream_t s, const float *min_z, const float *weight, 
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// Curvature pruning of the super-pillar planes ("Truncated Least Squares", preprocessor_utils.py:175-193):
+// for 100 decreasing thresholds, k-nearest-neighbour curvature of every surviving plane centre, drop the planes
+// whose mean curvature is not below the threshold.  One persistent CTA; the reference runs ~25 launches and a
+// blocking .max() per threshold.
+// ------------------------------------------------------------------------------------------------
+namespace pcs {
+
+constexpr int kPruneThreads = 1024;
+constexpr int kPruneMaxK = 16;
+
+__global__ void __launch_bounds__(kPruneThreads) plane_prune_kernel(const float *__restrict__ xyz,
+                                                                    const float *__restrict__ normal, int n, int K,
+                                                                    const float *__restrict__ thresholds, int n_thr,
+                                                                    int *__restrict__ keep) {
+  extern __shared__ float sm[];  // x[n], y[n], z[n], curv[n], active[n] (as int)
+  float *sx = sm, *sy = sm + n, *sz = sm + 2 * n, *curv = sm + 3 * n;
+  int *active = reinterpret_cast<int *>(sm + 4 * n);
+  __shared__ float s_max;
+  __shared__ int s_count, s_changed;
+  __shared__ float red[kPruneThreads / 32];
+  for (int i = threadIdx.x; i < n; i += kPruneThreads) {
+    sx[i] = xyz[i * 3 + 0];
+    sy[i] = xyz[i * 3 + 1];
+    sz[i] = xyz[i * 3 + 2];
+    active[i] = 1;
+  }
+  if (threadIdx.x == 0) {
+    s_count = n;
+    s_changed = 1;
+  }
+  __syncthreads();
+  for (int t = 0; t < n_thr; t++) {
+    if (s_count < K) break;  // fewer planes than neighbours: nothing left to compare (block-uniform)
+    if (s_changed) {
+      // curvature of every active plane from its K nearest active centres (self included, as knn(x, x) does)
+      for (int i = threadIdx.x; i < n; i += kPruneThreads) {
+        if (!active[i]) continue;
+        float bd[kPruneMaxK];
+        int bj[kPruneMaxK];
+        for (int k = 0; k < K; k++) {
+          bd[k] = 3.0e38f;
+          bj[k] = -1;
+        }
+        const float xi = sx[i], yi = sy[i], zi = sz[i];
+        for (int j = 0; j < n; j++) {
+          if (!active[j]) continue;
+          const float dx = sx[j] - xi, dy = sy[j] - yi, dz = sz[j] - zi;
+          const float d2 = dx * dx + dy * dy + dz * dz;
+          if (d2 < bd[K - 1]) {
+            int k = K - 1;
+            while (k > 0 && bd[k - 1] > d2) {
+              bd[k] = bd[k - 1];
+              bj[k] = bj[k - 1];
+              --k;
+            }
+            bd[k] = d2;
+            bj[k] = j;
+          }
+        }
+        const float nx = normal[i * 3 + 0], ny = normal[i * 3 + 1], nz = normal[i * 3 + 2];
+        float acc = 0.f;
+        for (int k = 0; k < K; k++) {
+          const int j = bj[k];
+          const float dx = sx[j] - xi, dy = sy[j] - yi, dz = sz[j] - zi;
+          const float p2p = fabsf(dx * nx + dy * ny + dz * nz);
+          acc += p2p / (sqrtf(dx * dx + dy * dy + dz * dz) + 1e-4f);
+        }
+        curv[i] = acc / (float)K;
+      }
+      __syncthreads();
+      float m = -3.0e38f;
+      for (int i = threadIdx.x; i < n; i += kPruneThreads)
+        if (active[i]) m = fmaxf(m, curv[i]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        float mm = -3.0e38f;
+        for (int w = 0; w < kPruneThreads / 32; w++) mm = fmaxf(mm, red[w]);
+        s_max = mm;
+        s_changed = 0;
+      }
+      __syncthreads();
+    }
+    const float thr = thresholds[t];
+    if (thr > s_max) continue;  // :186-187 (block-uniform)
+    __syncthreads();
+    int removed = 0;
+    for (int i = threadIdx.x; i < n; i += kPruneThreads)
+      if (active[i] && !(curv[i] < thr)) {
+        active[i] = 0;
+        removed++;
+      }
+    if (removed) {
+      atomicSub(&s_count, removed);
+      s_changed = 1;
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += kPruneThreads) keep[i] = active[i];
+}
+
+}  // namespace pcs
+
+extern "C" int pcs_plane_prune(pcs_stream_t s, const float *xyz, const float *normal, int n, int K,
+                               const float *thresholds, int n_thr, int32_t *keep) {
+  if (n < 1 || n > 8192 || K < 1 || K > pcs::kPruneMaxK || !xyz || !normal || !thresholds || !keep)
+    return pcs::set_error(PCS_ERR_BAD_ARG, "pcs_plane_prune: bad args (n <= 8192, K <= 16)");
+  size_t smem = (size_t)n * 5 * sizeof(float);
+  cudaFuncSetAttribute(pcs::plane_prune_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  PCS_LAUNCH(pcs::plane_prune_kernel, 1, pcs::kPruneThreads, smem, pcs::as_stream(s), xyz, normal, n, K, thresholds,
+             n_thr, keep);
+  return 0;
+}

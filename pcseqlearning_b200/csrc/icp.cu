@@ -311,7 +311,12 @@ __device__ void phase_scatter(const IcpArgs &A, const IcpGridGeom &geo, long lon
     const long long key = icp_key(geo, icp_coord(p.x, geo.lo[0], geo.vs[0]), icp_coord(p.y, geo.lo[1], geo.vs[1]),
                                   icp_coord(p.z, geo.lo[2], geo.vs[2]), icp_coord(p.w, geo.lo[3], geo.vs[3]));
     long long slot = hash_key(key) & A.mov_mask;
-    while (*((volatile long long *)&A.mov_table[slot].key) != key) slot = (slot + 1) & A.mov_mask;
+    long long probes = 0;
+    while (*((volatile long long *)&A.mov_table[slot].key) != key && probes <= A.mov_mask) {
+      slot = (slot + 1) & A.mov_mask;
+      ++probes;
+    }
+    if (probes > A.mov_mask) continue;  // insertion failed (flagged in counters[2])
     const int pos = atomicAdd(&A.mov_table[slot].start, 1);  // start becomes the END of the range (cursor mode)
     A.mov_sorted[pos] = p;
     A.mov_sidx[pos] = (int)i;

@@ -48,6 +48,20 @@ __device__ __forceinline__ float axis_gap(int o, float f, float u, float vs) {
   return g > 0.f ? g * vs : 0.f;
 }
 
+// ascending bitonic sort of one 64-bit key per lane
+__device__ __forceinline__ unsigned long long warp_sort_asc(unsigned long long v, int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const unsigned long long o = __shfl_xor_sync(kFull, v, j);
+      const bool take_min = (((lane & k) == 0) == ((lane & j) == 0));
+      v = take_min ? (o < v ? o : v) : (o > v ? o : v);
+    }
+  }
+  return v;
+}
+
 template <bool kFusedUF>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 radius_search_kernel(const pcs_slot_t *__restrict__ table, long long mask, const float4 *__restrict__ sorted_pts,
@@ -57,6 +71,7 @@ radius_search_kernel(const pcs_slot_t *__restrict__ table, long long mask, const
                      int *__restrict__ nbr_cnt, UfTargets uf, const int *__restrict__ skip_full_cnt) {
   __shared__ float4 s_lo[PCS_MAX_SEGMENTS];
   __shared__ long long s_dims[PCS_MAX_SEGMENTS * 4];
+  __shared__ unsigned long long s_list[kWarpsPerBlock][32];  // per-warp unsorted list while it is filling
   load_geom(g, s_lo, s_dims);
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -86,6 +101,10 @@ radius_search_kernel(const pcs_slot_t *__restrict__ table, long long mask, const
     unsigned long long best = kInf;  // lane j holds the j-th smallest (d2, index) key
     float worst_d2 = __int_as_float(0x7f800000);  // d2 of list entry K-1 (+inf while the list is not full)
     int fill = 0;                                 // number of valid list entries (<= K)
+    // While the list is not full, accepted candidates are simply appended (lane = fill + rank); the list is
+    // sorted once, when it fills up or at the end.  Only then does the insertion path below (with its K-th best
+    // threshold) take over.  Most sparse-region queries never fill their list and never pay for an insertion.
+    bool sorted = false;
 
     for (int cb = 0; cb < qr.nc; cb += 32) {
       // ---- 1. per-lane cell: offset, pruning bound, lookup -----------------------------------
@@ -154,6 +173,20 @@ radius_search_kernel(const pcs_slot_t *__restrict__ table, long long mask, const
           unsigned long long key64 = kInf;
           if (pass)
             key64 = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned int)__ldg(sorted_idx + cstart + j);
+          if (!sorted) {
+            const int npass = __popc(cand);
+            if (fill + npass <= K) {
+              // append: the passing lanes store their keys at list positions fill + rank (shared memory)
+              if (pass) s_list[warp][fill + __popc(cand & ((1u << lane) - 1u))] = key64;
+              fill += npass;
+              continue;
+            }
+            // overflow: bring the list into registers, order it, then insert with a threshold
+            __syncwarp();
+            best = lane < fill ? s_list[warp][lane] : kInf;
+            best = warp_sort_asc(best, lane);
+            sorted = true;
+          }
           unsigned long long worst = __shfl_sync(kFull, best, K - 1);
           while (cand) {
             const int srcl = __ffs(cand) - 1;
@@ -174,6 +207,12 @@ radius_search_kernel(const pcs_slot_t *__restrict__ table, long long mask, const
     }
 
     // ---- 4. emit ---------------------------------------------------------------------------------
+    if (!sorted) {
+      __syncwarp();
+      best = lane < fill ? s_list[warp][lane] : kInf;
+      if (fill > 1 && (nbr_idx || nbr_d2)) best = warp_sort_asc(best, lane);
+      __syncwarp();
+    }
     const int cnt = fill;
     const int idx = (int)(unsigned int)(best & 0xffffffffu);
     if (nbr_idx && lane < K) nbr_idx[q * K + lane] = lane < cnt ? idx : -1;

@@ -120,7 +120,12 @@ def compute_min_height_from_ransac(pillar_dims, num_pillars, voxels, pillars, cf
     # prune planes whose neighbourhood is curved ("Truncated Least Squares", :175-193)
     xyz, normal = best_center, best_normal
     K = cfg.K
-    for threshold in np.logspace(np.log(5) / np.log(10), np.log(0.01) / np.log(10), 100):
+    thresholds = np.logspace(np.log(5) / np.log(10), np.log(0.01) / np.log(10), 100)
+    if use_kernels and K <= xyz.shape[0] <= ops.PRUNE_MAX_PLANES and K <= 16:
+        keep = ops.plane_prune(xyz, normal, K, thresholds)  # the whole 100-threshold loop in one launch
+        xyz, normal = xyz[keep], normal[keep]
+        thresholds = []
+    for threshold in thresholds:
         e0, e1 = _knn_self(xyz, K)
         diff = xyz[e1] - xyz[e0]
         p2p = (diff * normal[e0]).sum(dim=-1).abs()

@@ -107,16 +107,26 @@ class SimpleReg(RegistrationTemplate):
         track = np.unique(obj_ids, return_inverse=True)[1]
         boxes.gt_box_track_label = torch.from_numpy(track).to(cls_label).long()
         seq_dict["obj_ids"] = obj_ids
+        # per-box speed = mean corner displacement to the previous box of the same trace (the first box of a trace
+        # copies the second, single-box traces get 0) -- the reference's per-trace loop (:79-92), all traces at once
         velo = torch.zeros_like(boxes.gt_box_attr[:, 0])
-        for trace_id in boxes.gt_box_track_label.unique().tolist():
-            m = (boxes.gt_box_track_label == trace_id).reshape(-1)
-            order = torch.argsort(boxes.gt_box_frame[m])
-            corners = boxes_to_corners_3d(boxes.gt_box_attr[m][order])
-            tv = torch.zeros_like(corners[:, 0, 0])
-            if tv.numel() > 1:
-                tv[1:] = (corners[1:] - corners[:-1]).norm(p=2, dim=-1).mean(dim=-1)
-                tv[0] = tv[1]
-            velo[m.nonzero()[:, 0][order]] = tv
+        nb = velo.shape[0]
+        if nb > 1:
+            key = boxes.gt_box_track_label.long() * (int(boxes.gt_box_frame.max().item()) + 2) + boxes.gt_box_frame.long()
+            order = torch.argsort(key, stable=True)
+            trk = boxes.gt_box_track_label[order]
+            corners = boxes_to_corners_3d(boxes.gt_box_attr[order])
+            step = (corners[1:] - corners[:-1]).norm(p=2, dim=-1).mean(dim=-1)
+            same_prev = torch.zeros(nb, dtype=torch.bool, device=velo.device)
+            same_prev[1:] = trk[1:] == trk[:-1]
+            v_sorted = torch.zeros_like(velo)
+            v_sorted[1:] = torch.where(same_prev[1:], step, torch.zeros_like(step))
+            first = ~same_prev
+            has_next = torch.zeros_like(first)
+            has_next[:-1] = same_prev[1:]
+            nxt = torch.roll(v_sorted, -1)
+            v_sorted = torch.where(first & has_next, nxt, v_sorted)
+            velo[order] = v_sorted
         boxes.gt_box_velo = velo
         boxes.moving = velo > 5e-2
         for key in boxes.keys():

@@ -189,3 +189,19 @@ def test_multi_radius_fused_equals_separate_searches(golden_dir):
     for lab, r in zip(labels, (1.25, 0.75, 0.25)):
         want, _ = ops.cluster_labels(pts, r, 32, chunk=10, num_frames=12)
         assert torch.equal(lab, want), r
+
+
+def test_compact_table_overflow_falls_back():
+    """A point set with one point per cell overflows the compact table; the grid must be rebuilt, not corrupted."""
+    from oracle import cpu_ops as oracle
+    from pcseqlearning_b200 import ops
+    rng = np.random.default_rng(31)
+    n = 6000
+    pts = np.zeros((n, 4), np.float32)
+    pts[:, 1:] = rng.uniform(0, 400, (n, 3))  # ~1 point per 0.3 m cell
+    t = _cuda(pts)
+    grid = ops.compact_grid(t, ops.radius_voxel_size(0.3))
+    assert grid.check() > n // 4 and grid.H >= 2 * n
+    labels, _ = ops.cluster_labels(t, 0.3, 32, chunk=10, num_frames=1)
+    want, _ = oracle.propose_clusters(pts, 0.3)
+    np.testing.assert_array_equal(labels.cpu().numpy(), want)
