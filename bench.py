@@ -211,6 +211,7 @@ def run_ours(args, rank, world, local_rank):
         "roofline": {"bound": "hbm", "kernel": "radius_search_kernel<fused union-find>", "achieved": round(achieved, 2),
                      "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": round(achieved / peak, 5),
                      "traffic": measured_traffic(), "launches_timed": len(durs), "mean_launch_ms": round(mean_ms, 4),
+                     "launch_ms": [round(d, 3) for d in durs[:6]],
                      "algorithmic_bytes_per_launch": alg_bytes,
                      "hash_build": {"achieved": round(hb_n * 28 / (hb_ms * 1e-3) / 1e9, 2) if hb else None,
                                     "mean_ms": round(hb_ms, 4), "algorithmic_bytes_per_launch": hb_n * 28}},

@@ -180,6 +180,7 @@ __device__ void ransac_step(const RansacArgs &A, long long v0, long long v1, int
   float dmax[kG];
 #pragma unroll
   for (int g = 0; g < kG; g++) dmax[g] = 0.f;
+  unsigned int viol = 0;  // warp-uniform: ratios for which this warp already found |dw| >= delta
   if (v1 > v0) {
     const int p_first = A.cidx[v0], p_last = A.cidx[v1 - 1];
     for (int g0 = p_first; g0 <= p_last; g0 += kGroup) {
@@ -276,18 +277,22 @@ __device__ void ransac_step(const RansacArgs &A, long long v0, long long v1, int
               float err;
               wnew = plane_weight(pn, p.y, p.z, p.w, A.sigma2, err);
               hit = err < sigma;
-              float wold;
-              const float *o = s_old[g][lp];
-              if (it == 0) {
-                wold = prior_weight(o[0], p.w, A.sigma2);
-              } else {
-                const float4 oa = *reinterpret_cast<const float4 *>(o);
-                const float2 ob = *reinterpret_cast<const float2 *>(o + 4);
-                const PlaneN po = {oa.x, oa.y, oa.z, oa.w, ob.x, ob.y};
-                float e2;
-                wold = plane_weight(po, p.y, p.z, p.w, A.sigma2, e2);
+              // The stopping rule only asks whether max|dw| < delta.  Once this warp has seen one voxel with
+              // |dw| >= delta for ratio g the answer is known, and the previous weight is no longer recomputed.
+              if (!((viol >> g) & 1u)) {
+                float wold;
+                const float *o = s_old[g][lp];
+                if (it == 0) {
+                  wold = prior_weight(o[0], p.w, A.sigma2);
+                } else {
+                  const float4 oa = *reinterpret_cast<const float4 *>(o);
+                  const float2 ob = *reinterpret_cast<const float2 *>(o + 4);
+                  const PlaneN po = {oa.x, oa.y, oa.z, oa.w, ob.x, ob.y};
+                  float e2;
+                  wold = plane_weight(po, p.y, p.z, p.w, A.sigma2, e2);
+                }
+                dmax[g] = fmaxf(dmax[g], fabsf(wnew - wold));
               }
-              dmax[g] = fmaxf(dmax[g], fabsf(wnew - wold));
             }
             if (uniform) {
               const float wx = wnew * xr, wy = wnew * yr, wz = wnew * zr;
@@ -318,6 +323,11 @@ __device__ void ransac_step(const RansacArgs &A, long long v0, long long v1, int
               if (hit) atomicAdd(nhit_next + (long long)(r0 + g) * A.C + pid, 1);
             }
           }
+        }
+        if (!first) {
+#pragma unroll
+          for (int g = 0; g < kG; g++)
+            if (!((viol >> g) & 1u) && __any_sync(0xffffffffu, dmax[g] >= A.stopping_delta)) viol |= 1u << g;
         }
       }
       if (cur >= 0) {

@@ -15,6 +15,8 @@
 //   4. the list is written as one coalesced row, or -- fused connected components -- the roots of
 //      the query and all its neighbours are hooked under their minimum in the union-find forest and
 //      no edge is ever written.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace pcs {
@@ -23,6 +25,7 @@ struct QueryRange {
   int qmin[4];
   int range[4];
   int nc;
+  int append;  // 1: append-then-sort list building, 0: sorted insertion from the first candidate
 };
 
 // Up to three union-find forests fed by one search (multi-radius cluster proposals): forest k receives the list
@@ -36,6 +39,7 @@ struct UfTargets {
 };
 
 constexpr int kWarpsPerBlock = 8;
+
 constexpr unsigned int kFull = 0xffffffffu;
 
 // lower bound (in metres) of |p_i - q_i| for points stored `o` cells away along one axis;
@@ -63,7 +67,7 @@ __device__ __forceinline__ unsigned long long warp_sort_asc(unsigned long long v
 }
 
 template <bool kFusedUF>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 5)
 radius_search_kernel(const pcs_slot_t *__restrict__ table, long long mask, const float4 *__restrict__ sorted_pts,
                      const int *__restrict__ sorted_idx, SegGeom g, const float4 *__restrict__ queries,
                      long long m, const int *__restrict__ order, QueryRange qr, const float *__restrict__ radius,
@@ -104,7 +108,7 @@ radius_search_kernel(const pcs_slot_t *__restrict__ table, long long mask, const
     // While the list is not full, accepted candidates are simply appended (lane = fill + rank); the list is
     // sorted once, when it fills up or at the end.  Only then does the insertion path below (with its K-th best
     // threshold) take over.  Most sparse-region queries never fill their list and never pay for an insertion.
-    bool sorted = false;
+    bool sorted = !qr.append;
 
     for (int cb = 0; cb < qr.nc; cb += 32) {
       // ---- 1. per-lane cell: offset, pruning bound, lookup -----------------------------------
@@ -230,7 +234,8 @@ radius_search_kernel(const pcs_slot_t *__restrict__ table, long long mask, const
         const int rmin = (int)__reduce_min_sync(kFull, (unsigned int)root);
         const unsigned int peers = __match_any_sync(kFull, root);
         if (root != rmin && lane == __ffs(peers) - 1) uf_unite(parent, root, rmin);
-        if (lane == 0) uf_unite(parent, (int)q, rmin);
+        // lanes without a neighbour carried the query itself; only a full warp of neighbours leaves it out
+        if (__all_sync(kFull, use) && lane == 0) uf_unite(parent, (int)q, rmin);
       }
     }
   }
@@ -287,6 +292,10 @@ int pcs_radius_search(pcs_stream_t s, const pcs_slot_t *table, int64_t H, const 
   if (m == 0) return 0;
   QueryRange qr;
   qr.nc = 1;
+  {
+    const char *e = getenv("PCS_SEARCH_APPEND");
+    qr.append = e ? atoi(e) : 1;
+  }
   for (int i = 0; i < 4; i++) {
     qr.qmin[i] = qmin[i];
     qr.range[i] = qmax[i] - qmin[i] + 1;

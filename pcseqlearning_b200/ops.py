@@ -152,7 +152,7 @@ class CellGrid:
         return coords, keys
 
     def search(self, query, K, radius, qmin=(0, -1, -1, -1), qmax=(0, 1, 1, 1), order=None, want_d2=False,
-               uf_parent=None, want_lists=True, uf_targets=None, skip_full_cnt=None):
+               uf_parent=None, want_lists=True, uf_targets=None, skip_full_cnt=None, cnt_out=None):
         """K nearest reference points within `radius` of every query (padded lists).
 
         query=None is the self-query mode: the grid's own points are the queries and are visited in
@@ -170,7 +170,7 @@ class CellGrid:
             m, dev = query.shape[0], query.device
         nbr_idx = torch.empty(m, K, dtype=torch.int32, device=dev) if want_lists else None
         nbr_d2 = torch.empty(m, K, dtype=torch.float32, device=dev) if (want_d2 and want_lists) else None
-        nbr_cnt = torch.empty(m, dtype=torch.int32, device=dev)
+        nbr_cnt = cnt_out if cnt_out is not None else torch.empty(m, dtype=torch.int32, device=dev)
         rad_t, rad_s = None, 0.0
         if isinstance(radius, torch.Tensor):
             rad_t = radius.float().contiguous()
@@ -556,12 +556,13 @@ def register_icp(mov_fxyz, mov_comp, mov_stationary, ref_fxyz, ref_stationary, n
 
 
 def cluster_labels_multi(fxyz, radii, max_num_neighbors=32, chunk=10, num_frames=None):
-    """Multi-radius fused cluster proposals: ONE fine search serves every radius.
+    """Multi-radius fused cluster proposals: a cascade of searches, finest radius first.
 
-    Pass A searches the finest radius on its own (reference-identical) grid.  A query whose list is full (K entries)
-    already holds its K nearest points overall, so the same list is united into the forests of all larger radii.
-    Pass B searches the coarsest radius only for the remaining (sparse-region) queries; intermediate radii take the
-    distance prefix of that list (top-K within r is the prefix of top-K within R >= r cut at d <= r).
+    Pass i searches radius r_i on its own (reference-identical) grid, but only for the queries whose list was not
+    full after pass i-1.  A query whose list is full (K entries) already holds its K nearest points overall, so the
+    same list is united into the forests of ALL larger radii and the query drops out of the cascade: the dense
+    regions -- the expensive ones for large cells -- are settled by the cheap fine search.
+    (Top-K within r is the prefix of top-K within R >= r cut at d <= r.)
     Returns ([labels per radius, in the order of `radii`], [n_comp per radius]).
     """
     fxyz = _as_points(fxyz, "point_fxyz")
@@ -572,16 +573,18 @@ def cluster_labels_multi(fxyz, radii, max_num_neighbors=32, chunk=10, num_frames
     n_seg = max(1, (num_frames + chunk - 1) // chunk)
     order = sorted(range(len(radii)), key=lambda i: radii[i])
     r_sorted = [float(radii[i]) for i in order]
-    if len(r_sorted) < 2 or len(r_sorted) > 3:
-        raise _lib.PcsError("cluster_labels_multi expects 2 or 3 radii")
-    r_fine, r_coarse = r_sorted[0], r_sorted[-1]
-    parents = [uf_new(n, fxyz.device) for _ in r_sorted]
-    fine = compact_grid(fxyz, radius_voxel_size(r_fine), seg_div=chunk, n_seg=n_seg)
-    targets = [(parents[0], r_fine, False)] + [(p, float("inf"), True) for p in parents[1:]]
-    _, cnt_fine, _ = fine.search(None, K, r_fine, uf_targets=targets, want_lists=False)
-    coarse = compact_grid(fxyz, radius_voxel_size(r_coarse), seg_div=chunk, n_seg=n_seg)
-    targets = [(p, r, False) for p, r in zip(parents[1:], r_sorted[1:])]
-    coarse.search(None, K, r_coarse, uf_targets=targets, want_lists=False, skip_full_cnt=cnt_fine)
+    if not (1 <= len(r_sorted) <= 3):
+        raise _lib.PcsError("cluster_labels_multi expects 1 to 3 radii")
+    # Edge sets grow with the radius (full lists are identical at every larger radius, the others are prefixes),
+    # so the forest of radius r_{i+1} is the forest of r_i plus the edges found by pass i+1: every pass feeds ONE
+    # forest and the next one starts from a copy of it.
+    parents = []
+    cnt = None
+    for i, r in enumerate(r_sorted):
+        parent = uf_new(n, fxyz.device) if i == 0 else parents[-1].clone()
+        grid = compact_grid(fxyz, radius_voxel_size(r), seg_div=chunk, n_seg=n_seg)
+        _, cnt, _ = grid.search(None, K, r, uf_parent=parent, want_lists=False, skip_full_cnt=cnt, cnt_out=cnt)
+        parents.append(parent)
     seg_of = point_segments(fxyz, chunk, n_seg)
     labels, n_comp = [None] * len(radii), [None] * len(radii)
     for pos, i in enumerate(order):
