@@ -216,6 +216,14 @@ int pcs_register_icp(pcs_stream_t s, const float *geo_lo, const float *geo_vs, c
 int pcs_plane_prune(pcs_stream_t s, const float *xyz, const float *normal, int n, int K, const float *thresholds,
                     int n_thr, int32_t *keep);
 
+/* Velocity smoothing of the tracker, smooth_velo (pcdet/models/registration/preprocessors/cluster_tracking.py:162-199):
+ * AdamW (torch defaults, lr 1e-2, MultiStepLR [100,200,300]) on velos[:, a..b, :2] with loss
+ * w0 * mean (v - d)^2 + w * mean |v[f] - v[f+1]| and the reference's 3-strike stopping rule, in one single-CTA launch.
+ * velos float[C][F][3] in/out (all elements receive AdamW's weight decay like the reference's parameter tensor),
+ * diffs float[C][F][3], m / v zero-filled scratch float[C * (b-a+1) * 2], info int32[2] = (iterations, stopped). */
+int pcs_smooth_velo(pcs_stream_t s, float *velos, const float *diffs, float *m, float *v, int C, int F, int a, int b,
+                    float w0, float w, int num_itr, float stopping, int32_t *info);
+
 #ifdef __cplusplus
 }
 #endif

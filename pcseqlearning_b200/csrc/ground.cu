@@ -789,3 +789,134 @@ extern "C" int pcs_plane_prune(pcs_stream_t s, const float *xyz, const float *no
              n_thr, keep);
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Velocity smoothing of the tracker (cluster_tracking.py:162-199): AdamW on the per-component xy velocities over
+// the frames [a, b]: loss = w0 * mean (v - d)^2 + w * mean |v[f] - v[f+1]|, lr 1e-2 with MultiStepLR([100,200,300]),
+// 3-strike stopping rule with a blocking loss.item() per iteration in the reference; here one persistent CTA.
+// torch.optim.AdamW decays EVERY element of the parameter tensor (also the ones without gradient); those only see
+// the accumulated factor prod(1 - lr_t * wd), applied once at the end.
+// ------------------------------------------------------------------------------------------------
+namespace pcs {
+
+struct VeloArgs {
+  float *velos;        // [C][F][3] in/out
+  const float *diffs;  // [C][F][3]
+  float *m;            // [C][nf][2] scratch (zeroed)
+  float *v;            // [C][nf][2] scratch (zeroed)
+  int *info;           // [2]: iterations run, stopped early
+  int C, F, a, b;
+  float w0, w;
+  int num_itr;
+  float stopping;
+};
+
+__global__ void __launch_bounds__(1024) smooth_velo_kernel(VeloArgs A) {
+  __shared__ double red[32];
+  __shared__ double s_loss;
+  const int nf = A.b - A.a + 1;
+  const int S = A.C * nf * 2;  // optimised elements: component, frame in [a, b], x/y
+  const float n1 = (float)S, n2 = (float)(A.C * (nf - 1) * 2);
+  float lr = 1e-2f;
+  const float beta1 = 0.9f, beta2 = 0.999f, eps = 1e-8f, wd = 1e-2f;
+  double b1t = 1.0, b2t = 1.0, decay = 1.0;
+  double last_loss = 1e10;
+  int countdown = 3, it = 0;
+#define VEL(c, f, k) A.velos[((long long)(c) * A.F + (f)) * 3 + (k)]
+  for (; it < A.num_itr; it++) {
+    double lsum = 0.0;
+    float g[24];
+    int nc = 0;
+    for (int e = threadIdx.x; e < S; e += blockDim.x, nc++) {
+      const int k = e & 1, fi = (e >> 1) % nf, c = (e >> 1) / nf, f = A.a + fi;
+      const float vv = VEL(c, f, k);
+      const float r = vv - A.diffs[((long long)c * A.F + f) * 3 + k];
+      float grad = A.w0 * 2.f * r / n1;
+      double l = (double)A.w0 * r * r / n1;
+      if (f < A.b) {
+        const float d = vv - VEL(c, f + 1, k);
+        grad += A.w * ((d > 0.f) - (d < 0.f)) / n2;
+        l += (double)A.w * fabsf(d) / n2;
+      }
+      if (f > A.a) {
+        const float d = VEL(c, f - 1, k) - vv;
+        grad -= A.w * ((d > 0.f) - (d < 0.f)) / n2;
+      }
+      g[nc] = grad;
+      lsum += l;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = lsum;
+    __syncthreads();  // all reads of the velocities are done
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += red[w];
+      s_loss = t;
+    }
+    b1t *= beta1;
+    b2t *= beta2;
+    const float bc1 = (float)(1.0 - b1t), bc2s = (float)sqrt(1.0 - b2t);
+    nc = 0;
+    for (int e = threadIdx.x; e < S; e += blockDim.x, nc++) {
+      const int k = e & 1, fi = (e >> 1) % nf, c = (e >> 1) / nf, f = A.a + fi;
+      const float grad = g[nc];
+      float p = VEL(c, f, k) * (1.f - lr * wd);
+      const float m = beta1 * A.m[e] + (1.f - beta1) * grad;
+      const float v = beta2 * A.v[e] + (1.f - beta2) * grad * grad;
+      A.m[e] = m;
+      A.v[e] = v;
+      p -= (lr / bc1) * (m / (sqrtf(v) / bc2s + eps));
+      VEL(c, f, k) = p;
+    }
+    decay *= (double)(1.f - lr * wd);
+    if (it + 1 == 100 || it + 1 == 200 || it + 1 == 300) lr *= 0.1f;  // MultiStepLR after scheduler.step()
+    __syncthreads();
+    const double loss = (double)(float)s_loss;
+    if (last_loss - loss < (double)A.stopping) countdown -= 1;
+    else countdown = 3;
+    if (countdown <= 0) {
+      ++it;
+      break;
+    }
+    last_loss = loss;
+  }
+  // elements without gradient: weight decay only
+  const long long total = (long long)A.C * A.F * 3;
+  const float dec = (float)decay;
+  for (long long e = threadIdx.x; e < total; e += blockDim.x) {
+    const int k = (int)(e % 3), f = (int)((e / 3) % A.F);
+    if (k < 2 && f >= A.a && f <= A.b) continue;
+    A.velos[e] *= dec;
+  }
+#undef VEL
+  if (threadIdx.x == 0) {
+    A.info[0] = it;
+    A.info[1] = countdown <= 0;
+  }
+}
+
+}  // namespace pcs
+
+extern "C" int pcs_smooth_velo(pcs_stream_t s, float *velos, const float *diffs, float *m, float *v, int C, int F,
+                               int a, int b, float w0, float w, int num_itr, float stopping, int32_t *info) {
+  if (!velos || !diffs || !m || !v || !info || C < 1 || a < 0 || b >= F || a >= b ||
+      (long long)C * (b - a + 1) * 2 > 24LL * 1024)
+    return pcs::set_error(PCS_ERR_BAD_ARG, "pcs_smooth_velo: bad args (a < b < F, C * (b-a+1) * 2 <= 24576)");
+  pcs::VeloArgs A;
+  A.velos = velos;
+  A.diffs = diffs;
+  A.m = m;
+  A.v = v;
+  A.info = info;
+  A.C = C;
+  A.F = F;
+  A.a = a;
+  A.b = b;
+  A.w0 = w0;
+  A.w = w;
+  A.num_itr = num_itr;
+  A.stopping = stopping;
+  PCS_LAUNCH(pcs::smooth_velo_kernel, 1, 1024, 0, pcs::as_stream(s), A);
+  return 0;
+}

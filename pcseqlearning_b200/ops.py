@@ -461,6 +461,24 @@ def plane_prune(xyz, normal, K, thresholds):
     return keep.bool()
 
 
+def smooth_velo(velos, diffs, a, b, weight0=1.0, weight=10.0, num_itr=300, stopping=1e-3):
+    """smooth_velo (cluster_tracking.py:162-199) in one launch; velos f32[C,F,3] is updated IN PLACE (a < b)."""
+    assert velos.is_contiguous() and velos.dtype == torch.float32
+    C, F, _ = velos.shape
+    dev = velos.device
+    diffs = diffs.float().contiguous()
+    S = C * (b - a + 1) * 2
+    m = torch.zeros(S, dtype=torch.float32, device=dev)
+    v = torch.zeros(S, dtype=torch.float32, device=dev)
+    info = torch.zeros(2, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev), _timed("smooth_velo", S=S):
+        _lib.check(_lib.lib().pcs_smooth_velo(_stream(), _ptr(velos), _ptr(diffs), _ptr(m), _ptr(v), C, F, int(a), int(b),
+                                              float(weight0), float(weight), int(num_itr), float(stopping), _ptr(info)),
+                   "pcs_smooth_velo")
+    return velos, info
+
+
+SMOOTH_VELO_MAX = 24 * 1024
 PRUNE_MAX_PLANES = 8192
 L1_MAX_CELLS = 65536
 

@@ -77,13 +77,19 @@ def filter_components(frame_points, max_diameter=STATIONARY_DIAMETER):
 
 
 def smooth_velo(_comp_velos, comp_center_diffs, frame_id, next_frame_id, weight0=1, weight=10, num_itr=300,
-                stopping=1e-3):
+                stopping=1e-3, use_kernels=True):
     """AdamW smoothing of the per-component xy velocities over [frame_id, next_frame_id]
     (cluster_tracking.py:162-199)."""
     if frame_id == next_frame_id:
         return _comp_velos
     if frame_id > next_frame_id:
         frame_id, next_frame_id = next_frame_id, frame_id
+    n_opt = _comp_velos.shape[0] * (next_frame_id - frame_id + 1) * 2
+    if use_kernels and _comp_velos.is_cuda and _comp_velos.is_contiguous() and n_opt <= ops.SMOOTH_VELO_MAX:
+        # the whole optimisation (<= 300 AdamW steps + stopping rule) in one single-CTA launch, in place like the
+        # reference's nn.Parameter that shares storage with the tensor
+        ops.smooth_velo(_comp_velos, comp_center_diffs, frame_id, next_frame_id, weight0, weight, num_itr, stopping)
+        return _comp_velos
     velos = nn.Parameter(_comp_velos, requires_grad=True)
     opt = torch.optim.AdamW([velos], lr=1e-2)
     sched = torch.optim.lr_scheduler.MultiStepLR(opt, [100, 200, 300])

@@ -65,3 +65,20 @@ def test_track_frame_vs_reference_python(golden_dir):
     assert jac_c > 0.95 and jac_p > 0.97, msg
     assert np.median(ang) < 1e-3 and np.median(dt) < 2e-2, msg  # metres at the component
     assert np.quantile(ang, 0.9) < 2e-2 and np.quantile(dt, 0.9) < 0.25, msg
+
+
+def test_smooth_velo_kernel_vs_torch_adamw():
+    """Fused velocity-smoothing kernel against the plain PyTorch AdamW loop it replaces."""
+    from pcseqlearning_b200.preprocessors.cluster_tracking import smooth_velo
+    g = torch.Generator(device="cuda").manual_seed(4)
+    C, F = 150, 17
+    for a, b in ((9, 12), (2, 8), (8, 9)):
+        base = torch.randn(C, 1, 3, generator=g, device="cuda") * 0.5
+        diffs = base + 0.05 * torch.randn(C, F, 3, generator=g, device="cuda")
+        velos = diffs + 0.1 * torch.randn(C, F, 3, generator=g, device="cuda")
+        v1 = smooth_velo(velos.clone(), diffs, a, b, use_kernels=True)
+        v2 = smooth_velo(velos.clone(), diffs, a, b, use_kernels=False)
+        d = (v1 - v2).abs()
+        assert float(d.max()) < 5e-3, (a, b, float(d.max()))
+        # untouched entries only see AdamW's weight decay
+        assert float((v1[:, :a] - v2[:, :a]).abs().max()) < 1e-5
