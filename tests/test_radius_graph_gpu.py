@@ -205,3 +205,19 @@ def test_compact_table_overflow_falls_back():
     labels, _ = ops.cluster_labels(t, 0.3, 32, chunk=10, num_frames=1)
     want, _ = oracle.propose_clusters(pts, 0.3)
     np.testing.assert_array_equal(labels.cpu().numpy(), want)
+
+
+def test_torch_hash_module_api_known_answer_and_chamfer():
+    """Module-style API of the op (torch_hash_modules.py): the reference's ndim=2 known-answer case and Chamfer."""
+    from pcseqlearning_b200.torch_hash import ChamferDistance, RadiusGraph
+    rg = RadiusGraph(ndim=2).cuda()
+    pts = torch.tensor([[0, 0.0, 0.0], [0, 0.1, 0.1], [0, 0.2, 0.2]], dtype=torch.float32).cuda()
+    eq, er = rg(pts, pts, 0.15, 1, sort_by_dist=True)
+    assert eq.tolist() == [0, 1, 2] and er.tolist() == [0, 1, 2]
+    g = torch.Generator(device="cuda").manual_seed(2)
+    a = torch.rand(5000, 4, generator=g, device="cuda") * 10
+    a[:, 0] = 0
+    b = a + 0.01
+    b[:, 0] = 0
+    cd = ChamferDistance(ndim=3)(a, b, 0.5)
+    assert abs(float(cd) - 2 * 3 * 0.01 ** 2) < 1e-5
