@@ -21,7 +21,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -52,32 +51,39 @@ def peaks():
     return 6650.0, "fallback"
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe).
+
+    ONE long-running `nvidia-smi -lms 200` child started before the timed region (forking a process that holds a CUDA
+    context from inside the timed loop would stall the Python thread that feeds the GPU)."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        super().__init__(daemon=True)
-        self.gpu, self.samples, self.stop_flag = gpu_index, [], False
+        self.gpu, self.proc = gpu_index, None
 
-    def run(self):
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.gpu)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            time.sleep(0.2)
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
 
     def summary(self):
-        self.stop_flag = True
+        lines = []
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+                out, _ = self.proc.communicate(timeout=5)
+                lines = [ln for ln in out.splitlines() if ln.strip()]
+            except Exception:
+                pass
         sm, mx, reasons = [], 0.0, set()
-        for s in self.samples:
+        for ln in lines:
+            s = [x.strip() for x in ln.split(",")]
             try:
                 sm.append(float(s[1]))
                 mx = max(mx, float(s[2]))

@@ -142,6 +142,46 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
   return v;
 }
 
+
+// ---- symmetric 3x3 eigen-decomposition, cyclic Jacobi from the identity, everything in registers ----------------
+// On return (d0, d1, d2) are the eigenvalues and v** the eigenvector matrix (columns), A = V diag(d) V^T.
+struct Eig3 {
+  double d0, d1, d2;
+  double v00, v01, v02, v10, v11, v12, v20, v21, v22;
+};
+
+#define PCS_JACOBI_ROT(app, aqq, apq, arp, arq, v0p, v0q, v1p, v1q, v2p, v2q)          \
+  if ((apq) != 0.0) {                                                                  \
+    const double theta = ((aqq) - (app)) / (2.0 * (apq));                              \
+    const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0)); \
+    const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;                              \
+    (app) -= t * (apq);                                                                \
+    (aqq) += t * (apq);                                                                \
+    (apq) = 0.0;                                                                       \
+    { const double x = (arp), y = (arq); (arp) = c * x - sn * y; (arq) = sn * x + c * y; } \
+    { const double x = (v0p), y = (v0q); (v0p) = c * x - sn * y; (v0q) = sn * x + c * y; } \
+    { const double x = (v1p), y = (v1q); (v1p) = c * x - sn * y; (v1q) = sn * x + c * y; } \
+    { const double x = (v2p), y = (v2q); (v2p) = c * x - sn * y; (v2q) = sn * x + c * y; } \
+  }
+
+__device__ __forceinline__ Eig3 jacobi_eig3(double a00, double a01, double a02, double a11, double a12, double a22) {
+  Eig3 e;
+  e.v00 = e.v11 = e.v22 = 1.0;
+  e.v01 = e.v02 = e.v10 = e.v12 = e.v20 = e.v21 = 0.0;
+  for (int sweep = 0; sweep < 30; sweep++) {
+    const double off = fabs(a01) + fabs(a02) + fabs(a12);
+    const double diag = fabs(a00) + fabs(a11) + fabs(a22);
+    if (off == 0.0 || off <= 1e-18 * diag) break;
+    PCS_JACOBI_ROT(a00, a11, a01, a02, a12, e.v00, e.v01, e.v10, e.v11, e.v20, e.v21)  // (p,q) = (0,1), r = 2
+    PCS_JACOBI_ROT(a00, a22, a02, a01, a12, e.v00, e.v02, e.v10, e.v12, e.v20, e.v22)  // (0,2), r = 1
+    PCS_JACOBI_ROT(a11, a22, a12, a01, a02, e.v01, e.v02, e.v11, e.v12, e.v21, e.v22)  // (1,2), r = 0
+  }
+  e.d0 = a00;
+  e.d1 = a11;
+  e.d2 = a22;
+  return e;
+}
+
 __device__ __forceinline__ void load_geom(const SegGeom &g, float4 *s_lo, long long *s_dims) {
   for (int i = threadIdx.x; i < g.n_seg; i += blockDim.x) {
     s_lo[i] = make_float4(g.lo[i * 4 + 0], g.lo[i * 4 + 1], g.lo[i * 4 + 2], g.lo[i * 4 + 3]);

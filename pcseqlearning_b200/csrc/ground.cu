@@ -19,44 +19,19 @@ namespace pcs {
 // 3x3 symmetric eigen-decomposition (cyclic Jacobi from the identity, like the batched syevj the reference
 // reaches through torch.linalg.eigh on CUDA).  Returns the eigenvector of the smallest eigenvalue.
 // ------------------------------------------------------------------------------------------------
-__device__ void smallest_eigvec3(const double a_in[6], float n_out[3]) {
+__device__ __forceinline__ void smallest_eigvec3(const double a_in[6], float n_out[3]) {
   // a = [xx, xy, xz, yy, yz, zz]
-  double a[3][3] = {{a_in[0], a_in[1], a_in[2]}, {a_in[1], a_in[3], a_in[4]}, {a_in[2], a_in[4], a_in[5]}};
-  double v[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
-  for (int sweep = 0; sweep < 30; sweep++) {
-    double off = fabs(a[0][1]) + fabs(a[0][2]) + fabs(a[1][2]);
-    double diag = fabs(a[0][0]) + fabs(a[1][1]) + fabs(a[2][2]);
-    if (off <= 1e-18 * diag || off == 0.0) break;
-    for (int p = 0; p < 2; p++)
-      for (int q = p + 1; q < 3; q++) {
-        double apq = a[p][q];
-        if (apq == 0.0) continue;
-        double theta = (a[q][q] - a[p][p]) / (2.0 * apq);
-        double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-        double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
-        for (int k = 0; k < 3; k++) {  // A <- A J
-          double akp = a[k][p], akq = a[k][q];
-          a[k][p] = c * akp - s * akq;
-          a[k][q] = s * akp + c * akq;
-        }
-        for (int k = 0; k < 3; k++) {  // A <- J^T A
-          double apk = a[p][k], aqk = a[q][k];
-          a[p][k] = c * apk - s * aqk;
-          a[q][k] = s * apk + c * aqk;
-        }
-        for (int k = 0; k < 3; k++) {  // V <- V J
-          double vkp = v[k][p], vkq = v[k][q];
-          v[k][p] = c * vkp - s * vkq;
-          v[k][q] = s * vkp + c * vkq;
-        }
-      }
-  }
+  const Eig3 e = jacobi_eig3(a_in[0], a_in[1], a_in[2], a_in[3], a_in[4], a_in[5]);
   int m = 0;
-  if (a[1][1] < a[m][m]) m = 1;
-  if (a[2][2] < a[m][m]) m = 2;
-  n_out[0] = (float)v[0][m];
-  n_out[1] = (float)v[1][m];
-  n_out[2] = (float)v[2][m];
+  double dm = e.d0;
+  if (e.d1 < dm) {
+    m = 1;
+    dm = e.d1;
+  }
+  if (e.d2 < dm) m = 2;
+  n_out[0] = (float)(m == 0 ? e.v00 : (m == 1 ? e.v01 : e.v02));
+  n_out[1] = (float)(m == 0 ? e.v10 : (m == 1 ? e.v11 : e.v12));
+  n_out[2] = (float)(m == 0 ? e.v20 : (m == 1 ? e.v21 : e.v22));
 }
 
 constexpr int kAcc = 10;         // S0, S1[3], S2[6]

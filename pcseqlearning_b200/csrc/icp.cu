@@ -185,70 +185,56 @@ __device__ int nn_search_warp(const IcpGridGeom &g, const pcs_slot_t *table, lon
 // A is well conditioned here (the regulariser adds angle_reg * R_prev), so U = A V S^-1 from the eigen-decomposition
 // of A^T A is accurate; R is the unique polar factor whatever the ordering / signs of the decomposition.
 __device__ void kabsch_rotation(const double A[9], double R[9]) {
-  double B[3][3];
-  for (int i = 0; i < 3; i++)
-    for (int j = 0; j < 3; j++) B[i][j] = A[0 * 3 + i] * A[0 * 3 + j] + A[1 * 3 + i] * A[1 * 3 + j] + A[2 * 3 + i] * A[2 * 3 + j];
-  double V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
-  for (int sweep = 0; sweep < 40; sweep++) {
-    const double off = fabs(B[0][1]) + fabs(B[0][2]) + fabs(B[1][2]);
-    const double diag = fabs(B[0][0]) + fabs(B[1][1]) + fabs(B[2][2]);
-    if (off <= 1e-30 + 1e-17 * diag) break;
-    for (int p = 0; p < 2; p++)
-      for (int q = p + 1; q < 3; q++) {
-        const double bpq = B[p][q];
-        if (bpq == 0.0) continue;
-        const double theta = (B[q][q] - B[p][p]) / (2.0 * bpq);
-        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-        const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
-        for (int k = 0; k < 3; k++) {
-          const double bkp = B[k][p], bkq = B[k][q];
-          B[k][p] = c * bkp - s * bkq;
-          B[k][q] = s * bkp + c * bkq;
-        }
-        for (int k = 0; k < 3; k++) {
-          const double bpk = B[p][k], bqk = B[q][k];
-          B[p][k] = c * bpk - s * bqk;
-          B[q][k] = s * bpk + c * bqk;
-        }
-        for (int k = 0; k < 3; k++) {
-          const double vkp = V[k][p], vkq = V[k][q];
-          V[k][p] = c * vkp - s * vkq;
-          V[k][q] = s * vkp + c * vkq;
-        }
-      }
+  // B = A^T A (symmetric), eigen-decomposition B = V diag(s^2) V^T
+  double b00 = 0, b01 = 0, b02 = 0, b11 = 0, b12 = 0, b22 = 0;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const double x = A[k * 3 + 0], y = A[k * 3 + 1], z = A[k * 3 + 2];
+    b00 += x * x;
+    b01 += x * y;
+    b02 += x * z;
+    b11 += y * y;
+    b12 += y * z;
+    b22 += z * z;
   }
+  const Eig3 e = jacobi_eig3(b00, b01, b02, b11, b12, b22);
+  double ev[3] = {e.d0, e.d1, e.d2};
+  double V[3][3] = {{e.v00, e.v01, e.v02}, {e.v10, e.v11, e.v12}, {e.v20, e.v21, e.v22}};
   // order singular values descending so that the reflection fix lands on the smallest one
-  int idx[3] = {0, 1, 2};
-  for (int a = 0; a < 2; a++)
-    for (int b = a + 1; b < 3; b++)
-      if (B[idx[b]][idx[b]] > B[idx[a]][idx[a]]) {
-        int t = idx[a];
-        idx[a] = idx[b];
-        idx[b] = t;
-      }
+  int i0 = 0, i1 = 1, i2 = 2;
+  if (ev[i1] > ev[i0]) { int t = i0; i0 = i1; i1 = t; }
+  if (ev[i2] > ev[i0]) { int t = i0; i0 = i2; i2 = t; }
+  if (ev[i2] > ev[i1]) { int t = i1; i1 = i2; i2 = t; }
+  const int idx[3] = {i0, i1, i2};
   double Vs[3][3], U[3][3];
+#pragma unroll
   for (int j = 0; j < 3; j++) {
-    const double sv = sqrt(fmax(B[idx[j]][idx[j]], 0.0));
+    const double sv = sqrt(fmax(ev[idx[j]], 0.0));
+#pragma unroll
     for (int i = 0; i < 3; i++) Vs[i][j] = V[i][idx[j]];
+#pragma unroll
     for (int i = 0; i < 3; i++) {
       const double av = A[i * 3 + 0] * Vs[0][j] + A[i * 3 + 1] * Vs[1][j] + A[i * 3 + 2] * Vs[2][j];
       U[i][j] = sv > 1e-300 ? av / sv : 0.0;
     }
   }
-  if (!(B[idx[2]][idx[2]] > 1e-24 * fmax(B[idx[0]][idx[0]], 1e-300))) {
+  if (!(ev[i2] > 1e-24 * fmax(ev[i0], 1e-300))) {
     // rank-deficient A: complete U with the cross product of its first two columns
     U[0][2] = U[1][0] * U[2][1] - U[2][0] * U[1][1];
     U[1][2] = U[2][0] * U[0][1] - U[0][0] * U[2][1];
     U[2][2] = U[0][0] * U[1][1] - U[1][0] * U[0][1];
   }
-  // M = V U^T ; d = det(M)
+  // M = V U^T ; d = det(M) is the third sign entry, as in the reference (:172)
   double M[3][3];
+#pragma unroll
   for (int i = 0; i < 3; i++)
+#pragma unroll
     for (int j = 0; j < 3; j++) M[i][j] = Vs[i][0] * U[j][0] + Vs[i][1] * U[j][1] + Vs[i][2] * U[j][2];
-  const double det = M[0][0] * (M[1][1] * M[2][2] - M[1][2] * M[2][1]) - M[0][1] * (M[1][0] * M[2][2] - M[1][2] * M[2][0]) +
-                     M[0][2] * (M[1][0] * M[2][1] - M[1][1] * M[2][0]);
-  const double d = det;  // the reference uses det itself as the third sign entry (:172)
+  const double d = M[0][0] * (M[1][1] * M[2][2] - M[1][2] * M[2][1]) - M[0][1] * (M[1][0] * M[2][2] - M[1][2] * M[2][0]) +
+                   M[0][2] * (M[1][0] * M[2][1] - M[1][1] * M[2][0]);
+#pragma unroll
   for (int i = 0; i < 3; i++)
+#pragma unroll
     for (int j = 0; j < 3; j++) R[i * 3 + j] = Vs[i][0] * U[j][0] + Vs[i][1] * U[j][1] + d * Vs[i][2] * U[j][2];
 }
 
