@@ -212,9 +212,10 @@ int pcs_register_icp(pcs_stream_t s, const float *geo_lo, const float *geo_vs, c
 
 /* Curvature pruning of plane centres ("Truncated Least Squares", preprocessor_utils.py:175-193): for every threshold
  * (descending), kNN (self included) mean curvature of the surviving planes; planes with curvature >= threshold are
- * dropped whenever threshold <= max curvature.  One persistent CTA.  xyz / normal float[n][3], keep int32[n] out. */
+ * dropped whenever threshold <= max curvature.  One cooperative launch (grid barriers only around rounds that remove
+ * planes).  xyz / normal float[n][3], keep int32[n] out, curv float[n] scratch, state uint32[4] zero-filled scratch. */
 int pcs_plane_prune(pcs_stream_t s, const float *xyz, const float *normal, int n, int K, const float *thresholds,
-                    int n_thr, int32_t *keep);
+                    int n_thr, int32_t *keep, float *curv, uint32_t *state);
 
 /* Velocity smoothing of the tracker, smooth_velo (pcdet/models/registration/preprocessors/cluster_tracking.py:162-199):
  * AdamW (torch defaults, lr 1e-2, MultiStepLR [100,200,300]) on velos[:, a..b, :2] with loss
@@ -223,6 +224,11 @@ int pcs_plane_prune(pcs_stream_t s, const float *xyz, const float *normal, int n
  * diffs float[C][F][3], m / v zero-filled scratch float[C * (b-a+1) * 2], info int32[2] = (iterations, stopped). */
 int pcs_smooth_velo(pcs_stream_t s, float *velos, const float *diffs, float *m, float *v, int C, int F, int a, int b,
                     float w0, float w, int num_itr, float stopping, int32_t *info);
+
+/* Row gather dst[i] = src[idx[i]] (rows of 1 / 4 / 8 / 12 / 16 bytes, int64 indices): the re-ordering after the
+ * subsample (simple_reg.py:126-130), the ground-mask filter (ground_plane_remover.py:238-247) and the voxel -> point
+ * broadcast of the ground stage (preprocessor_utils.py:416-419). */
+int pcs_gather_rows(pcs_stream_t s, const void *src, const int64_t *idx, int64_t n, int row_bytes, void *dst);
 
 #ifdef __cplusplus
 }

@@ -272,3 +272,56 @@ int pcs_point_segments(pcs_stream_t s, const float *pts, int64_t n, int seg_div,
 }
 
 }  // extern "C"
+
+// ---- row gather -------------------------------------------------------------------------------------------------
+// dst[i] = src[idx[i]] for rows of 1 / 4 / 8 / 12 / 16 bytes (int64 indices).  Replaces the fancy-indexing passes of
+// the host code (simple_reg.py:126-130 re-ordering after the subsample, ground_plane_remover.py:238-247 mask filter,
+// preprocessor_utils.py:416-419 voxel -> point broadcast): one coalesced index load, one (random) vector load and one
+// coalesced vector store per row.
+namespace pcs {
+
+template <typename T>
+__global__ void __launch_bounds__(256) gather_rows_kernel(const T *__restrict__ src, const long long *__restrict__ idx,
+                                                          long long n, T *__restrict__ dst) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) dst[i] = src[idx[i]];
+}
+
+struct Row12 {
+  float a, b, c;
+};
+
+}  // namespace pcs
+
+extern "C" int pcs_gather_rows(pcs_stream_t s, const void *src, const int64_t *idx, int64_t n, int row_bytes, void *dst) {
+  using namespace pcs;
+  if (n < 0 || (n > 0 && (!src || !idx || !dst))) return set_error(PCS_ERR_BAD_ARG, "pcs_gather_rows: bad args");
+  if (n == 0) return 0;
+  const int grid = grid_for(n, 256, 16);
+  cudaStream_t st = as_stream(s);
+  const long long *ix = (const long long *)idx;
+  switch (row_bytes) {
+    case 1:
+      PCS_LAUNCH(gather_rows_kernel<unsigned char>, grid, 256, 0, st, (const unsigned char *)src, ix, (long long)n,
+                 (unsigned char *)dst);
+      break;
+    case 4:
+      PCS_LAUNCH(gather_rows_kernel<int>, grid, 256, 0, st, (const int *)src, ix, (long long)n, (int *)dst);
+      break;
+    case 8:
+      PCS_LAUNCH(gather_rows_kernel<long long>, grid, 256, 0, st, (const long long *)src, ix, (long long)n,
+                 (long long *)dst);
+      break;
+    case 12:
+      PCS_LAUNCH(gather_rows_kernel<Row12>, grid, 256, 0, st, (const Row12 *)src, ix, (long long)n, (Row12 *)dst);
+      break;
+    case 16:
+      if (((uintptr_t)src & 15) || ((uintptr_t)dst & 15)) return set_error(PCS_ERR_BAD_ARG, "pcs_gather_rows: alignment");
+      PCS_LAUNCH(gather_rows_kernel<int4>, grid, 256, 0, st, (const int4 *)src, ix, (long long)n, (int4 *)dst);
+      break;
+    default:
+      return set_error(PCS_ERR_BAD_ARG, "pcs_gather_rows: row size must be 1, 4, 8, 12 or 16 bytes");
+  }
+  return 0;
+}

@@ -655,35 +655,39 @@ int pcs_l1_heightfield(pcs_stream_t s, const float *min_z, const float *weight, 
 // ------------------------------------------------------------------------------------------------
 namespace pcs {
 
-constexpr int kPruneThreads = 1024;
+constexpr int kPruneThreads = 64;
 constexpr int kPruneMaxK = 16;
+constexpr int kPruneMaxN = 8192;
 
+// state (global, zero-initialised by the caller): [0] / [2] max-curvature bits of even / odd evaluation rounds (the
+// slot of the next round is cleared while nobody uses it), [1] removed count
 __global__ void __launch_bounds__(kPruneThreads) plane_prune_kernel(const float *__restrict__ xyz,
                                                                     const float *__restrict__ normal, int n, int K,
                                                                     const float *__restrict__ thresholds, int n_thr,
-                                                                    int *__restrict__ keep) {
-  extern __shared__ float sm[];  // x[n], y[n], z[n], curv[n], active[n] (as int)
-  float *sx = sm, *sy = sm + n, *sz = sm + 2 * n, *curv = sm + 3 * n;
-  int *active = reinterpret_cast<int *>(sm + 4 * n);
-  __shared__ float s_max;
-  __shared__ int s_count, s_changed;
-  __shared__ float red[kPruneThreads / 32];
-  for (int i = threadIdx.x; i < n; i += kPruneThreads) {
+                                                                    int *__restrict__ keep, float *__restrict__ curv,
+                                                                    unsigned int *__restrict__ state) {
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ float sm[];  // x[n], y[n], z[n], active[n]
+  float *sx = sm, *sy = sm + n, *sz = sm + 2 * n;
+  int *active = reinterpret_cast<int *>(sm + 3 * n);
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
     sx[i] = xyz[i * 3 + 0];
     sy[i] = xyz[i * 3 + 1];
     sz[i] = xyz[i * 3 + 2];
     active[i] = 1;
   }
-  if (threadIdx.x == 0) {
-    s_count = n;
-    s_changed = 1;
-  }
+  for (int i = gtid; i < n; i += gthreads) keep[i] = 1;
   __syncthreads();
+  int count = n, round = 0;
+  bool changed = true;
+  float maxc = 0.f;
   for (int t = 0; t < n_thr; t++) {
-    if (s_count < K) break;  // fewer planes than neighbours: nothing left to compare (block-uniform)
-    if (s_changed) {
-      // curvature of every active plane from its K nearest active centres (self included, as knn(x, x) does)
-      for (int i = threadIdx.x; i < n; i += kPruneThreads) {
+    if (count < K) break;  // fewer planes than neighbours (grid-uniform)
+    if (changed) {
+      // curvature of my active planes from their K nearest active centres (self included, like knn(x, x))
+      float m = 0.f;
+      for (int i = gtid; i < n; i += gthreads) {
         if (!active[i]) continue;
         float bd[kPruneMaxK];
         int bj[kPruneMaxK];
@@ -712,57 +716,61 @@ __global__ void __launch_bounds__(kPruneThreads) plane_prune_kernel(const float 
         for (int k = 0; k < K; k++) {
           const int j = bj[k];
           const float dx = sx[j] - xi, dy = sy[j] - yi, dz = sz[j] - zi;
-          const float p2p = fabsf(dx * nx + dy * ny + dz * nz);
-          acc += p2p / (sqrtf(dx * dx + dy * dy + dz * dz) + 1e-4f);
+          acc += fabsf(dx * nx + dy * ny + dz * nz) / (sqrtf(dx * dx + dy * dy + dz * dz) + 1e-4f);
         }
-        curv[i] = acc / (float)K;
+        const float c = acc / (float)K;
+        curv[i] = c;
+        m = fmaxf(m, c);
       }
-      __syncthreads();
-      float m = -3.0e38f;
-      for (int i = threadIdx.x; i < n; i += kPruneThreads)
-        if (active[i]) m = fmaxf(m, curv[i]);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-      if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        float mm = -3.0e38f;
-        for (int w = 0; w < kPruneThreads / 32; w++) mm = fmaxf(mm, red[w]);
-        s_max = mm;
-        s_changed = 0;
-      }
-      __syncthreads();
+      unsigned int *slot = state + ((round & 1) ? 2 : 0);
+      if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(slot, __float_as_uint(m));
+      grid.sync();
+      maxc = __uint_as_float(__ldcg(slot));
+      changed = false;
+      ++round;
     }
+    if (thresholds[t] > maxc) continue;  // :186-187; nothing changes, no barrier needed
+    // remove every plane whose curvature is not below the threshold (at least the arg-max goes)
     const float thr = thresholds[t];
-    if (thr > s_max) continue;  // :186-187 (block-uniform)
-    __syncthreads();
     int removed = 0;
-    for (int i = threadIdx.x; i < n; i += kPruneThreads)
-      if (active[i] && !(curv[i] < thr)) {
-        active[i] = 0;
+    for (int i = gtid; i < n; i += gthreads)
+      if (active[i] && !(__ldcg(curv + i) < thr)) {
+        keep[i] = 0;
         removed++;
       }
-    if (removed) {
-      atomicSub(&s_count, removed);
-      s_changed = 1;
-    }
+    if (removed) atomicAdd(state + 1, (unsigned int)removed);
+    if (gtid == 0) state[(round & 1) ? 2 : 0] = 0u;  // slot of the NEXT evaluation round (idle since two barriers)
+    grid.sync();
+    count = n - (int)__ldcg(state + 1);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) active[i] = __ldcg(keep + i);
     __syncthreads();
+    changed = true;
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < n; i += kPruneThreads) keep[i] = active[i];
 }
 
 }  // namespace pcs
 
 extern "C" int pcs_plane_prune(pcs_stream_t s, const float *xyz, const float *normal, int n, int K,
-                               const float *thresholds, int n_thr, int32_t *keep) {
-  if (n < 1 || n > 8192 || K < 1 || K > pcs::kPruneMaxK || !xyz || !normal || !thresholds || !keep)
-    return pcs::set_error(PCS_ERR_BAD_ARG, "pcs_plane_prune: bad args (n <= 8192, K <= 16)");
-  size_t smem = (size_t)n * 5 * sizeof(float);
-  cudaFuncSetAttribute(pcs::plane_prune_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  PCS_LAUNCH(pcs::plane_prune_kernel, 1, pcs::kPruneThreads, smem, pcs::as_stream(s), xyz, normal, n, K, thresholds,
-             n_thr, keep);
-  return 0;
+                               const float *thresholds, int n_thr, int32_t *keep, float *curv, uint32_t *state) {
+  using namespace pcs;
+  if (n < 1 || n > kPruneMaxN || K < 1 || K > kPruneMaxK || !xyz || !normal || !thresholds || !keep || !curv || !state)
+    return set_error(PCS_ERR_BAD_ARG, "pcs_plane_prune: bad args (n <= 8192, K <= 16)");  // state: uint32[4]
+  size_t smem = (size_t)n * 4 * sizeof(float);
+  cudaFuncSetAttribute(plane_prune_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int blocks = (n + kPruneThreads - 1) / kPruneThreads;
+  if (blocks > sms) blocks = sms;
+  void *args[] = {(void *)&xyz, (void *)&normal, (void *)&n, (void *)&K, (void *)&thresholds, (void *)&n_thr,
+                  (void *)&keep, (void *)&curv, (void *)&state};
+  cudaError_t e = cudaLaunchCooperativeKernel((void *)plane_prune_kernel, dim3(blocks), dim3(kPruneThreads), args, smem,
+                                              as_stream(s));
+  g_launches++;
+  if (e != cudaSuccess) return set_error((int)e, "plane_prune_kernel (cooperative launch)");
+  return check_launch("plane_prune_kernel");
 }
 
 // ------------------------------------------------------------------------------------------------

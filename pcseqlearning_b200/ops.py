@@ -455,9 +455,12 @@ def plane_prune(xyz, normal, K, thresholds):
     n, dev = xyz.shape[0], xyz.device
     thr = torch.as_tensor(np.asarray(thresholds, dtype=np.float32), device=dev)
     keep = torch.empty(n, dtype=torch.int32, device=dev)
+    curv = torch.zeros(n, dtype=torch.float32, device=dev)
+    state = torch.zeros(4, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev), _timed("plane_prune", n=n):
         _lib.check(_lib.lib().pcs_plane_prune(_stream(), _ptr(xyz), _ptr(normal), n, int(K), _ptr(thr),
-                                              int(thr.shape[0]), _ptr(keep)), "pcs_plane_prune")
+                                              int(thr.shape[0]), _ptr(keep), _ptr(curv), _ptr(state)),
+                   "pcs_plane_prune")
     return keep.bool()
 
 
@@ -608,6 +611,23 @@ def cluster_labels_multi(fxyz, radii, max_num_neighbors=32, chunk=10, num_frames
     for pos, i in enumerate(order):
         n_comp[i], labels[i] = uf_labels(parents[pos], seg_of, n_seg)
     return labels, n_comp
+
+
+def gather_rows(src, idx):
+    """src[idx] for a contiguous tensor whose rows are 1, 4, 8, 12 or 16 bytes (anything else falls back to torch
+    indexing).  idx: int64 row indices."""
+    if not src.is_cuda or not src.is_contiguous() or src.dim() == 0:
+        return src[idx]
+    row_bytes = src.element_size() * (src[0].numel() if src.dim() > 1 else 1)
+    if row_bytes not in (1, 4, 8, 12, 16) or (row_bytes == 16 and src.data_ptr() % 16):
+        return src[idx]
+    idx = idx.long().contiguous()
+    n = idx.shape[0]
+    out = torch.empty((n,) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
+    with torch.cuda.device(src.device):
+        _lib.check(_lib.lib().pcs_gather_rows(_stream(), _ptr(src), _ptr(idx), n, int(row_bytes), _ptr(out)),
+                   "pcs_gather_rows")
+    return out
 
 
 def launch_count():

@@ -4,6 +4,7 @@ import os
 import torch
 from torch import nn
 
+from .. import ops
 from ..utils import EasyDict, Timer
 from .ground_utils import ground_plane_removal
 
@@ -62,12 +63,12 @@ class GroundPlaneRemover(nn.Module):
                 self.output_stats(seq_dict["segmentation_label"], ground_mask, sequence_id,
                                   self.model_cfg.LOG_DIR + f"/height{h}")
         seq_dict["point_height"] = height
-        keep = ~ground_mask
+        keep_rows = (~ground_mask).nonzero().reshape(-1)  # one index list shared by every filtered array
         for key in ["point_fxyz", "segmentation_label", "point_sweep", "point_height", "instance_label",
                     "point_horizon"]:
             if key in seq_dict:
-                seq_dict[f"full_{key}"] = seq_dict[key].clone()
-                seq_dict[key] = seq_dict[key][keep]
+                seq_dict[f"full_{key}"] = seq_dict[key]  # the filtered copy below never aliases the full array
+                seq_dict[key] = ops.gather_rows(seq_dict[key], keep_rows)
         return seq_dict
 
     def extra_repr(self):

@@ -102,7 +102,7 @@ def compute_min_height_from_ransac(pillar_dims, num_pillars, voxels, pillars, cf
     ratios = torch.linspace(0.3, 1, 30)
     if use_kernels:
         # all 30 x <=50 IRLS iterations inside one persistent cooperative launch
-        best_center, best_normal, best_conf, _ = ops.ground_ransac(voxels.bxyz[order], cidx, num_coarse, c_min_z,
+        best_center, best_normal, best_conf, _ = ops.ground_ransac(ops.gather_rows(voxels.bxyz, order), cidx, num_coarse, c_min_z,
                                                                    c_max_z, ratios, cfg.SIGMA2)
     else:
         sigma = cfg.SIGMA2 ** 0.5
@@ -224,5 +224,5 @@ def ground_plane_removal(point_fxyz, cfg, warmup=None, use_kernels=True):
     v_horizon = voxels.bxyz[:, -1] > v_min_z
     v_height = voxels.bxyz[:, -1] - v_height
     fitting_error = v_height - v_min_z
-    return (v_height[point_voxel_index], v_horizon[point_voxel_index], fitting_error[point_voxel_index],
-            pillars.height, pillars.min_z)
+    return (ops.gather_rows(v_height, point_voxel_index), ops.gather_rows(v_horizon, point_voxel_index),
+            ops.gather_rows(fitting_error, point_voxel_index), pillars.height, pillars.min_z)

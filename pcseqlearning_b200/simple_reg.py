@@ -156,7 +156,7 @@ class SimpleReg(RegistrationTemplate):
                 for key in ["point_fxyz", "point_feat", "segmentation_label", "instance_label", "is_foreground",
                             "point_sweep"]:
                     if key in seq_dict:
-                        seq_dict[key] = seq_dict[key][pick]
+                        seq_dict[key] = ops.gather_rows(seq_dict[key], pick)
             for key in ["gt_box_cls_label", "gt_box_attr", "augmented", "num_points_in_gt", "gt_boxes", "obj_ids",
                         "frame_id", "pose", "top_lidar_origin", "num_sweeps", "gt_box_corners_3d", "gt_box_velo"]:
                 if key in batch_dict:
