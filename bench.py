@@ -152,17 +152,26 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    step_ms = []
+
     def timed(fn, steps):
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
         a.record()
-        for _ in range(steps):
+        for i in range(steps):
             torch.cuda.nvtx.range_push("pcs_step")  # lets ncu restrict a launch list to the timed region
             res = fn()
             torch.cuda.nvtx.range_pop()
+            marks[i].record()
         b.record()
         barrier()
         ms = a.elapsed_time(b)
+        step_ms.clear()
+        prev = a
+        for m in marks:
+            step_ms.append(round(prev.elapsed_time(m), 2))
+            prev = m
         if world > 1:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -177,6 +186,7 @@ def run_ours(args, rank, world, local_rank):
     ops.enable_event_log(True)
     ops.reset_launch_count()
     ms_dev, seq = timed(step_device, args.steps)
+    dev_step_ms = list(step_ms)
     launches = ops.launch_count()
     log = ops.event_log()
     ops.enable_event_log(False)
@@ -202,7 +212,8 @@ def run_ours(args, rank, world, local_rank):
     e2e = frames_total / (ms_e2e / args.steps / 1e3)
     line = {
         "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": round(ms_dev / args.steps, 3), "higher_is_better": True,
+        "warmup": max(args.warmup, 3), "ms_per_step": round(ms_dev / args.steps, 3), "step_ms": dev_step_ms,
+        "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "frames": args.frames, "points_per_sequence": n_points,
                    "points_after_subsample": int(seq["full_point_fxyz"].shape[0]),

@@ -36,7 +36,7 @@ __device__ __forceinline__ void smallest_eigvec3(const double a_in[6], float n_o
 
 constexpr int kAcc = 10;         // S0, S1[3], S2[6]
 constexpr int kRansacThreads = 256;
-constexpr int kGroup = 32;       // super-pillars whose planes a block keeps in shared memory at a time
+constexpr int kGroup = 128;      // super-pillars whose planes a block keeps in shared memory at a time
 constexpr int kG = 3;            // height ratios processed together by one team of blocks
 constexpr int kMaxRatios = 32;
 
