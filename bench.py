@@ -124,7 +124,14 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     t0 = time.time()
-    batch = generate_sequence(rank, num_frames=args.frames, device=dev)
+    # every rank processes the SAME synthetic sequence (identical work per GPU: replicas / weak scaling)
+    cache = args.cache and f"{args.cache}.f{args.frames}.pt"
+    if cache and os.path.exists(cache):
+        batch = torch.load(cache, map_location=dev, weights_only=False)
+    else:
+        batch = generate_sequence(0, num_frames=args.frames, device=dev)
+        if cache and rank == 0:
+            torch.save(batch, cache)
     torch.cuda.synchronize()
     n_points = int(batch["point_bxyz"].shape[0])
     gen_s = time.time() - t0
@@ -234,7 +241,7 @@ def run_ours(args, rank, world, local_rank):
                                     "mean_ms": round(hb_ms, 4), "algorithmic_bytes_per_launch": hb_n * 28}},
         "clocks": clocks,
     }
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(batch, args, sample_frames=args.cpu_frames)
     if rank == 0:
         print(json.dumps(line), flush=True)
@@ -331,6 +338,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=198)
     ap.add_argument("--cpu-frames", type=int, default=2, dest="cpu_frames")
+    ap.add_argument("--cache", default=None, help="path prefix to cache the synthetic sequence (profiling runs)")
+    ap.add_argument("--no-cpu-baseline", action="store_true", dest="no_cpu")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
