@@ -17,6 +17,7 @@ N > 1 (torchrun, one rank per GPU): every rank processes its own sequence (repli
 path has no data-path collective at sequence granularity.
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -52,19 +53,71 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe).
+    """SM clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe).
 
-    ONE long-running `nvidia-smi -lms 200` child started before the timed region (forking a process that holds a CUDA
-    context from inside the timed loop would stall the Python thread that feeds the GPU)."""
+    Default: an in-process NVML thread (two light queries every 50 ms).  A looping `nvidia-smi` child is the fallback
+    (PCS_BENCH_CLOCKS=smi): its full per-iteration query holds driver locks long enough to show up as occasional
+    +30..150 ms steps on this host-synchronising path."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.gpu, self.proc = gpu_index, None
+        self.gpu, self.proc, self.thread = gpu_index, None, None
+        self.mode = os.environ.get("PCS_BENCH_CLOCKS", "nvml")
+        self.sm, self.mx, self.reasons, self.stop = [], 0.0, set(), False
+
+    def _nvml_handle(self):
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(self.gpu).uuid)
+            if not uuid.startswith("GPU-"):
+                uuid = "GPU-" + uuid
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+        except Exception:
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.gpu]) if vis and vis.split(",")[self.gpu].isdigit() else self.gpu
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(idx)
+
+    def _nvml_loop(self, nv, h):
+        bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown")
+                else nv.nvmlClocksThrottleReasonHwSlowdown,
+                "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown",
+                                               getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40)),
+                "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown",
+                                               getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20)),
+                "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap",
+                                        getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4))}
+        reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons",
+                             getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons", None))
+        while not self.stop:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                if reasons_fn is not None:
+                    r = int(reasons_fn(h))
+                    for name, bit in bits.items():
+                        if r & int(bit):
+                            self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.05)
 
     def start(self):
+        if self.mode == "off":
+            return
+        if self.mode == "nvml":
+            try:
+                nv, h = self._nvml_handle()
+                self.mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+                import threading
+                self.thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+                self.thread.start()
+                return
+            except Exception:
+                self.thread = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-i", str(self.gpu), "-lms", "200"], stdout=subprocess.PIPE,
@@ -73,6 +126,12 @@ class ClockSampler:
             self.proc = None
 
     def summary(self):
+        if self.thread is not None:
+            self.stop = True
+            self.thread.join(timeout=2)
+            sm = sorted(self.sm)
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.mx or None,
+                    "reasons": sorted(self.reasons), "samples": len(sm), "source": "nvml"}
         lines = []
         if self.proc is not None:
             try:
@@ -94,7 +153,7 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi"}
 
 
 def build_model(device):
@@ -162,17 +221,30 @@ def run_ours(args, rank, world, local_rank):
     step_ms = []
 
     def timed(fn, steps):
+        # like timeit: no cyclic-GC pass inside the timed loop (a full collection of the torch-sized heap is a
+        # 100-200 ms host stall that lands on one early step and never again)
+        gc.collect()
+        gc.disable()
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
         a.record()
         for i in range(steps):
             torch.cuda.nvtx.range_push("pcs_step")  # lets ncu restrict a launch list to the timed region
-            res = fn()
+            t0 = time.perf_counter()
+            res = None  # the previous step's result is released first (the trainer does not keep it either); holding
+            res = fn()  # it makes the caching allocator cudaMalloc ~1 GB mid-run, a 100-200 ms stall on one step
             torch.cuda.nvtx.range_pop()
             marks[i].record()
+            if os.environ.get("PCS_BENCH_DIAG"):
+                st = torch.cuda.memory_stats()
+                print("[diag] step %d host %.1f ms, cudaMalloc calls %d, reserved %.2f GB, retries %d" % (
+                    i, (time.perf_counter() - t0) * 1e3, st.get("num_device_alloc", -1),
+                    st.get("reserved_bytes.all.current", 0) / 1e9, st.get("num_alloc_retries", -1)),
+                    file=sys.stderr, flush=True)
         b.record()
         barrier()
+        gc.enable()
         ms = a.elapsed_time(b)
         step_ms.clear()
         prev = a
@@ -186,7 +258,9 @@ def run_ours(args, rank, world, local_rank):
         return ms, res
 
     for _ in range(max(args.warmup, 3)):
+        seq = None
         seq = step_device()
+    seq = None
     torch.cuda.synchronize()
     sampler = ClockSampler(local_rank)
     sampler.start()

@@ -73,10 +73,13 @@ int pcs_voxel_keys(pcs_stream_t s, const float *pts, int64_t n, int seg_div, int
  *   table[H]        open addressing over unique cell keys (H = power of two)
  *   sorted_pts[n]   float4 points grouped by cell, sorted_idx[n] their original row index
  *   counters int32[4]: [0] number of occupied cells, [1] scatter cursor, [2] error flag, [3] unused
- * The table must NOT be pre-filled; the call clears it. */
+ *   occ        optional uint32[occ_bits / 32] occupancy bitmap (occ_bits = power of two in [32, 2^32]): one bit per
+ *              occupied cell at position hash(key) >> (32 - log2 occ_bits).  A search given the same bitmap rejects
+ *              most empty neighbour cells with one 4-byte load instead of a probe sequence (no false negatives).
+ * The table and bitmap must NOT be pre-filled; the call clears them. */
 int pcs_hash_build(pcs_stream_t s, const float *pts, int64_t n, int seg_div, int n_seg, const float *seg_lo,
                    const int64_t *seg_dims, const float *vs, pcs_slot_t *table, int64_t H, float *sorted_pts,
-                   int32_t *sorted_idx, int32_t *counters);
+                   int32_t *sorted_idx, int32_t *counters, uint32_t *occ, int64_t occ_bits);
 
 /* ---- neighbour search -----------------------------------------------------------------------
  * Replaces radius_graph_gpu = count_radius_graph_degree_kernel + radius_graph_kernel
@@ -96,14 +99,15 @@ int pcs_hash_build(pcs_stream_t s, const float *pts, int64_t n, int seg_div, int
  *              materialised); with uf_need_full[k] set it is only fed by queries whose list is full (count == K):
  *              for those the K nearest within this radius are also the K nearest within any larger radius, which
  *              is how ONE fine search serves several proposal radii (multi-radius search).
- *   skip_full_cnt optional int32[m]: counts of a previous (finer) pass; queries with count >= K are skipped. */
+ *   skip_full_cnt optional int32[m]: counts of a previous (finer) pass; queries with count >= K are skipped.
+ *   occ, occ_bits optional occupancy bitmap written by pcs_hash_build for this table (NULL / 0 = not used). */
 int pcs_radius_search(pcs_stream_t s, const pcs_slot_t *table, int64_t H, const float *sorted_pts,
                       const int32_t *sorted_idx, int seg_div, int n_seg, const float *seg_lo,
                       const int64_t *seg_dims, const float *vs, const float *queries, int64_t m,
                       const int32_t *order, const int *qmin, const int *qmax, const float *radius,
                       float radius_scalar, int K, int32_t *nbr_idx, float *nbr_d2, int32_t *nbr_cnt,
                       int32_t *const *uf_parents, const float *uf_r2, const int *uf_need_full, int n_uf,
-                      const int32_t *skip_full_cnt);
+                      const int32_t *skip_full_cnt, const uint32_t *occ, int64_t occ_bits);
 
 /* Exclusive scan int32 -> int64 with the grand total at out[n] (out has n+1 entries).
  * Replaces `cumsum(degree) - degree` (torch_hash_kernel.cu:534-538) without the two blocking .item(). */

@@ -26,11 +26,11 @@ _SIGNATURES = {
     "pcs_voxel_keys": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_void_p]),
     "pcs_hash_build": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
-                               c_int64, c_void_p, c_void_p, c_void_p]),
+                               c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64]),
     "pcs_radius_search": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
                                   c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
-                                  c_void_p]),
+                                  c_void_p, c_void_p, c_int64]),
     "pcs_exclusive_scan": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64]),
     "pcs_exclusive_scan_tmp_bytes": (c_int64, [c_int64]),
     "pcs_lists_to_edges": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p,

@@ -133,17 +133,20 @@ __global__ void __launch_bounds__(256) voxel_keys_kernel(const float4 *__restric
 // hash build: clear -> count (find-or-insert unique cell keys) -> assign ranges -> scatter
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) table_clear_kernel(int4 *__restrict__ table, long long H,
-                                                          int *__restrict__ counters) {
+                                                          int *__restrict__ counters, unsigned int *__restrict__ occ,
+                                                          long long occ_words) {
   long long stride = (long long)gridDim.x * blockDim.x;
   const int4 e = make_int4(-1, -1, 0, 0);  // key = -1, start = 0, count = 0
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < H; i += stride) table[i] = e;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < occ_words; i += stride) occ[i] = 0u;
   if (blockIdx.x == 0 && threadIdx.x < 4) counters[threadIdx.x] = 0;
 }
 
 // find-or-insert; returns the slot.  Plain load first (most points land in an existing cell).
 __device__ __forceinline__ long long find_or_insert(pcs_slot_t *table, long long mask, long long key,
-                                                    int *counters) {
-  long long slot = hash_key(key) & mask;
+                                                    int *counters, unsigned int *occ, int occ_shift) {
+  const unsigned int h = hash_key(key);
+  long long slot = h & mask;
   for (long long probes = 0; probes <= mask; ++probes) {
     long long cur = *((volatile long long *)&table[slot].key);
     if (cur == key) return slot;
@@ -152,6 +155,10 @@ __device__ __forceinline__ long long find_or_insert(pcs_slot_t *table, long long
                                           (unsigned long long)PCS_EMPTY_KEY, (unsigned long long)key);
       if (prev == (unsigned long long)PCS_EMPTY_KEY) {
         atomicAdd(&counters[0], 1);
+        if (occ) {  // the claimer publishes the cell in the occupancy bitmap
+          const unsigned int b = h >> occ_shift;
+          atomicOr(&occ[b >> 5], 1u << (b & 31));
+        }
         return slot;
       }
       if ((long long)prev == key) return slot;
@@ -166,7 +173,8 @@ __device__ __forceinline__ long long find_or_insert(pcs_slot_t *table, long long
 // spatially coherent points issues one probe sequence and one atomicAdd per distinct cell.
 __global__ void __launch_bounds__(256) hash_count_kernel(const float4 *__restrict__ pts, long long n, SegGeom g,
                                                          pcs_slot_t *__restrict__ table, long long mask,
-                                                         int *__restrict__ counters) {
+                                                         int *__restrict__ counters, unsigned int *__restrict__ occ,
+                                                         int occ_shift) {
   __shared__ float4 s_lo[PCS_MAX_SEGMENTS];
   __shared__ long long s_dims[PCS_MAX_SEGMENTS * 4];
   load_geom(g, s_lo, s_dims);
@@ -186,7 +194,7 @@ __global__ void __launch_bounds__(256) hash_count_kernel(const float4 *__restric
     unsigned int peers = __match_any_sync(0xffffffffu, key);
     int leader = __ffs(peers) - 1;
     if (valid && lane == leader) {
-      long long slot = find_or_insert(table, mask, key, counters);
+      long long slot = find_or_insert(table, mask, key, counters, occ, occ_shift);
       if (slot >= 0) atomicAdd(&table[slot].count, __popc(peers));
     }
   }
@@ -331,16 +339,25 @@ int pcs_voxel_keys(pcs_stream_t s, const float *pts, int64_t n, int seg_div, int
 
 int pcs_hash_build(pcs_stream_t s, const float *pts, int64_t n, int seg_div, int n_seg, const float *seg_lo,
                    const int64_t *seg_dims, const float *vs, pcs_slot_t *table, int64_t H, float *sorted_pts,
-                   int32_t *sorted_idx, int32_t *counters) {
+                   int32_t *sorted_idx, int32_t *counters, uint32_t *occ, int64_t occ_bits) {
+  if (occ && (occ_bits < 32 || occ_bits > (1LL << 32) || (occ_bits & (occ_bits - 1))))
+    return set_error(PCS_ERR_BAD_ARG, "pcs_hash_build: occ_bits must be a power of two in [32, 2^32]");
+  int occ_shift = 0;
+  if (occ) {
+    int lg = 0;
+    while ((1LL << lg) < occ_bits) ++lg;
+    occ_shift = 32 - lg;
+  }
   if (!table || !counters || H < 2 || (H & (H - 1)) || n_seg < 1 || n_seg > PCS_MAX_SEGMENTS || n < 0 ||
       n >= (1LL << 31) || ((uintptr_t)pts & 15) || ((uintptr_t)sorted_pts & 15) || ((uintptr_t)table & 15))
     return set_error(PCS_ERR_BAD_ARG, "pcs_hash_build: bad args (H must be a power of two, buffers 16-byte aligned)");
   cudaStream_t st = as_stream(s);
   SegGeom g = make_geom(seg_lo, seg_dims, vs, seg_div, n_seg);
-  PCS_LAUNCH(table_clear_kernel, grid_for(H, 256, 8), 256, 0, st, (int4 *)table, (long long)H, counters);
+  PCS_LAUNCH(table_clear_kernel, grid_for(H, 256, 8), 256, 0, st, (int4 *)table, (long long)H, counters, occ,
+             occ ? (long long)(occ_bits >> 5) : 0LL);
   if (n == 0) return 0;
   PCS_LAUNCH(hash_count_kernel, grid_for(n, 256, 8), 256, 0, st, (const float4 *)pts, (long long)n, g, table,
-             (long long)(H - 1), counters);
+             (long long)(H - 1), counters, occ, occ_shift);
   PCS_LAUNCH(assign_ranges_kernel, (unsigned)((H + 1023) / 1024), 256, 0, st, table, (long long)H, counters);
   PCS_LAUNCH(hash_scatter_kernel, grid_for(n, 256, 8), 256, 0, st, (const float4 *)pts, (long long)n, g, table,
              (long long)(H - 1), (float4 *)sorted_pts, sorted_idx);

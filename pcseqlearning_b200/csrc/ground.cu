@@ -660,7 +660,11 @@ constexpr int kPruneMaxK = 16;
 constexpr int kPruneMaxN = 8192;
 
 // state (global, zero-initialised by the caller): [0] / [2] max-curvature bits of even / odd evaluation rounds (the
-// slot of the next round is cleared while nobody uses it), [1] removed count
+// slot of the next round is cleared while nobody uses it), [1] removed count.
+// Every thread owns at most one plane (the launch uses ceil(n / 64) <= 128 CTAs).  A plane's curvature only changes
+// when one of its K nearest centres is removed, so after the first round only those "dirty" planes are re-evaluated;
+// a dirty plane is handled by its whole warp: K selection passes over the active centres, each picking the next
+// smallest (d2, index) pair -- the order the reference's knn returns them in.
 __global__ void __launch_bounds__(kPruneThreads) plane_prune_kernel(const float *__restrict__ xyz,
                                                                     const float *__restrict__ normal, int n, int K,
                                                                     const float *__restrict__ thresholds, int n_thr,
@@ -668,64 +672,77 @@ __global__ void __launch_bounds__(kPruneThreads) plane_prune_kernel(const float 
                                                                     unsigned int *__restrict__ state) {
   cg::grid_group grid = cg::this_grid();
   extern __shared__ float sm[];  // x[n], y[n], z[n], active[n]
+  __shared__ int s_nb[kPruneMaxK][kPruneThreads];  // neighbour lists of this CTA's planes
   float *sx = sm, *sy = sm + n, *sz = sm + 2 * n;
   int *active = reinterpret_cast<int *>(sm + 3 * n);
-  const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    sx[i] = xyz[i * 3 + 0];
-    sy[i] = xyz[i * 3 + 1];
-    sz[i] = xyz[i * 3 + 2];
-    active[i] = 1;
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // my plane
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    sx[j] = xyz[j * 3 + 0];
+    sy[j] = xyz[j * 3 + 1];
+    sz[j] = xyz[j * 3 + 2];
+    active[j] = 1;
   }
-  for (int i = gtid; i < n; i += gthreads) keep[i] = 1;
+  if (i < n) keep[i] = 1;
   __syncthreads();
+  const bool mine = i < n;
+  bool alive = mine, dirty = mine;
+  float c = 0.f;
+  float nx = 0.f, ny = 0.f, nz = 0.f;
+  if (mine) {
+    nx = normal[i * 3 + 0];
+    ny = normal[i * 3 + 1];
+    nz = normal[i * 3 + 2];
+  }
   int count = n, round = 0;
   bool changed = true;
   float maxc = 0.f;
   for (int t = 0; t < n_thr; t++) {
     if (count < K) break;  // fewer planes than neighbours (grid-uniform)
     if (changed) {
-      // curvature of my active planes from their K nearest active centres (self included, like knn(x, x))
-      float m = 0.f;
-      for (int i = gtid; i < n; i += gthreads) {
-        if (!active[i]) continue;
-        float bd[kPruneMaxK];
-        int bj[kPruneMaxK];
-        for (int k = 0; k < K; k++) {
-          bd[k] = 3.0e38f;
-          bj[k] = -1;
-        }
-        const float xi = sx[i], yi = sy[i], zi = sz[i];
-        for (int j = 0; j < n; j++) {
-          if (!active[j]) continue;
-          const float dx = sx[j] - xi, dy = sy[j] - yi, dz = sz[j] - zi;
-          const float d2 = dx * dx + dy * dy + dz * dz;
-          if (d2 < bd[K - 1]) {
-            int k = K - 1;
-            while (k > 0 && bd[k - 1] > d2) {
-              bd[k] = bd[k - 1];
-              bj[k] = bj[k - 1];
-              --k;
-            }
-            bd[k] = d2;
-            bj[k] = j;
-          }
-        }
-        const float nx = normal[i * 3 + 0], ny = normal[i * 3 + 1], nz = normal[i * 3 + 2];
+      unsigned int todo = __ballot_sync(0xffffffffu, alive && dirty);
+      while (todo) {
+        const int d = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int pi = __shfl_sync(0xffffffffu, i, d);
+        const float xi = sx[pi], yi = sy[pi], zi = sz[pi];
+        const float pnx = __shfl_sync(0xffffffffu, nx, d), pny = __shfl_sync(0xffffffffu, ny, d),
+                    pnz = __shfl_sync(0xffffffffu, nz, d);
+        unsigned int last_d = 0u;
+        int last_j = -1;  // (d2 bits, index) of the previously selected neighbour
         float acc = 0.f;
         for (int k = 0; k < K; k++) {
-          const int j = bj[k];
-          const float dx = sx[j] - xi, dy = sy[j] - yi, dz = sz[j] - zi;
-          acc += fabsf(dx * nx + dy * ny + dz * nz) / (sqrtf(dx * dx + dy * dy + dz * dz) + 1e-4f);
+          unsigned int bd = 0xffffffffu;
+          int bj = 0x7fffffff;
+          for (int j = lane; j < n; j += 32) {
+            if (!active[j]) continue;
+            const float dx = sx[j] - xi, dy = sy[j] - yi, dz = sz[j] - zi;
+            const unsigned int db = __float_as_uint(dx * dx + dy * dy + dz * dz);
+            const bool after = db > last_d || (db == last_d && j > last_j);
+            if (after && (db < bd || (db == bd && j < bj))) {
+              bd = db;
+              bj = j;
+            }
+          }
+          const unsigned int wd = __reduce_min_sync(0xffffffffu, bd);
+          const int wj = __reduce_min_sync(0xffffffffu, bd == wd ? bj : 0x7fffffff);
+          last_d = wd;
+          last_j = wj;
+          if (lane == d) s_nb[k][threadIdx.x] = wj;
+          const float dx = sx[wj] - xi, dy = sy[wj] - yi, dz = sz[wj] - zi;
+          acc += fabsf(dx * pnx + dy * pny + dz * pnz) / (sqrtf(dx * dx + dy * dy + dz * dz) + 1e-4f);
         }
-        const float c = acc / (float)K;
-        curv[i] = c;
-        m = fmaxf(m, c);
+        if (lane == d) {
+          c = acc / (float)K;
+          curv[i] = c;
+          dirty = false;
+        }
       }
+      float m = alive ? c : 0.f;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
       unsigned int *slot = state + ((round & 1) ? 2 : 0);
-      if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(slot, __float_as_uint(m));
+      if (lane == 0 && m > 0.f) atomicMax(slot, __float_as_uint(m));
       grid.sync();
       maxc = __uint_as_float(__ldcg(slot));
       changed = false;
@@ -734,18 +751,20 @@ __global__ void __launch_bounds__(kPruneThreads) plane_prune_kernel(const float 
     if (thresholds[t] > maxc) continue;  // :186-187; nothing changes, no barrier needed
     // remove every plane whose curvature is not below the threshold (at least the arg-max goes)
     const float thr = thresholds[t];
-    int removed = 0;
-    for (int i = gtid; i < n; i += gthreads)
-      if (active[i] && !(__ldcg(curv + i) < thr)) {
-        keep[i] = 0;
-        removed++;
-      }
-    if (removed) atomicAdd(state + 1, (unsigned int)removed);
-    if (gtid == 0) state[(round & 1) ? 2 : 0] = 0u;  // slot of the NEXT evaluation round (idle since two barriers)
+    const bool drop = alive && !(c < thr);
+    if (drop) keep[i] = 0;
+    const unsigned int dropped = __ballot_sync(0xffffffffu, drop);
+    if (lane == 0 && dropped) atomicAdd(state + 1, (unsigned int)__popc(dropped));
+    if (i == 0) state[(round & 1) ? 2 : 0] = 0u;  // slot of the NEXT evaluation round (idle since two barriers)
     grid.sync();
     count = n - (int)__ldcg(state + 1);
-    for (int i = threadIdx.x; i < n; i += blockDim.x) active[i] = __ldcg(keep + i);
+    for (int j = threadIdx.x; j < n; j += blockDim.x) active[j] = __ldcg(keep + j);
     __syncthreads();
+    if (mine) {
+      alive = active[i] != 0;
+      if (alive && !dirty)
+        for (int k = 0; k < K; k++) dirty |= !active[s_nb[k][threadIdx.x]];
+    }
     changed = true;
   }
 }
@@ -762,8 +781,8 @@ extern "C" int pcs_plane_prune(pcs_stream_t s, const float *xyz, const float *no
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  int blocks = (n + kPruneThreads - 1) / kPruneThreads;
-  if (blocks > sms) blocks = sms;
+  int blocks = (n + kPruneThreads - 1) / kPruneThreads;  // one plane per thread
+  if (blocks > sms) return set_error(PCS_ERR_BAD_ARG, "pcs_plane_prune: more planes than co-resident threads");
   void *args[] = {(void *)&xyz, (void *)&normal, (void *)&n, (void *)&K, (void *)&thresholds, (void *)&n_thr,
                   (void *)&keep, (void *)&curv, (void *)&state};
   cudaError_t e = cudaLaunchCooperativeKernel((void *)plane_prune_kernel, dim3(blocks), dim3(kPruneThreads), args, smem,

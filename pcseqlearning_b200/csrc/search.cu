@@ -72,7 +72,8 @@ radius_search_kernel(const pcs_slot_t *__restrict__ table, long long mask, const
                      const int *__restrict__ sorted_idx, SegGeom g, const float4 *__restrict__ queries,
                      long long m, const int *__restrict__ order, QueryRange qr, const float *__restrict__ radius,
                      float radius_scalar, int K, int *__restrict__ nbr_idx, float *__restrict__ nbr_d2,
-                     int *__restrict__ nbr_cnt, UfTargets uf, const int *__restrict__ skip_full_cnt) {
+                     int *__restrict__ nbr_cnt, UfTargets uf, const int *__restrict__ skip_full_cnt,
+                     const unsigned int *__restrict__ occ, int occ_shift) {
   __shared__ float4 s_lo[PCS_MAX_SEGMENTS];
   __shared__ long long s_dims[PCS_MAX_SEGMENTS * 4];
   __shared__ unsigned long long s_list[kWarpsPerBlock][32];  // per-warp unsorted list while it is filling
@@ -138,17 +139,25 @@ radius_search_kernel(const pcs_slot_t *__restrict__ table, long long mask, const
         }
         if (dmin2 <= r2) {
           const long long key = map2key4(c0, c1, c2, c3, dims) | ((long long)seg << PCS_SEG_SHIFT);
-          long long slot = hash_key(key) & mask;
-          for (long long probes = 0; probes <= mask; ++probes) {
-            const int4 v = __ldg(reinterpret_cast<const int4 *>(table + slot));
-            const long long k = ((long long)v.y << 32) | (unsigned int)v.x;
-            if (k == key) {
-              start = v.z;
-              count = v.w;
-              break;
+          const unsigned int h = hash_key(key);
+          bool maybe = true;
+          if (occ) {  // occupancy bitmap: most empty neighbour cells are rejected here, without a probe sequence
+            const unsigned int b = h >> occ_shift;
+            maybe = (__ldg(occ + (b >> 5)) >> (b & 31)) & 1u;
+          }
+          if (maybe) {
+            const int klo = (int)(unsigned int)key, khi = (int)(key >> 32);
+            unsigned int slot = h & (unsigned int)mask;
+            for (unsigned int probes = 0; probes <= (unsigned int)mask; ++probes) {
+              const int4 v = __ldg(reinterpret_cast<const int4 *>(table + slot));
+              if (v.x == klo && v.y == khi) {
+                start = v.z;
+                count = v.w;
+                break;
+              }
+              if ((v.x & v.y) == -1) break;  // PCS_EMPTY_KEY
+              slot = (slot + 1) & (unsigned int)mask;
             }
-            if (k == PCS_EMPTY_KEY) break;
-            slot = (slot + 1) & mask;
           }
           if (count > 0) sel = (__float_as_uint(dmin2) & ~31u) | (unsigned int)lane;
         }
@@ -274,8 +283,16 @@ int pcs_radius_search(pcs_stream_t s, const pcs_slot_t *table, int64_t H, const 
                       const int32_t *order, const int *qmin, const int *qmax, const float *radius,
                       float radius_scalar, int K, int32_t *nbr_idx, float *nbr_d2, int32_t *nbr_cnt,
                       int32_t *const *uf_parents, const float *uf_r2, const int *uf_need_full, int n_uf,
-                      const int32_t *skip_full_cnt) {
-  if (!table || H < 2 || (H & (H - 1)) || K < 1 || K > PCS_MAX_K || n_seg < 1 || n_seg > PCS_MAX_SEGMENTS ||
+                      const int32_t *skip_full_cnt, const uint32_t *occ, int64_t occ_bits) {
+  if (occ && (occ_bits < 32 || occ_bits > (1LL << 32) || (occ_bits & (occ_bits - 1))))
+    return set_error(PCS_ERR_BAD_ARG, "pcs_radius_search: occ_bits must be a power of two in [32, 2^32]");
+  int occ_shift = 0;
+  if (occ) {
+    int lg = 0;
+    while ((1LL << lg) < occ_bits) ++lg;
+    occ_shift = 32 - lg;
+  }
+  if (!table || H < 2 || H > (1LL << 31) || (H & (H - 1)) || K < 1 || K > PCS_MAX_K || n_seg < 1 || n_seg > PCS_MAX_SEGMENTS ||
       !qmin || !qmax || ((uintptr_t)queries & 15) || ((uintptr_t)sorted_pts & 15) || m < 0 || m >= (1LL << 31))
     return set_error(PCS_ERR_BAD_ARG, "pcs_radius_search: bad args (1 <= K <= 32, 16-byte aligned points)");
   if (n_uf < 0 || n_uf > 3 || (n_uf > 0 && (!uf_parents || !uf_r2 || !uf_need_full)))
@@ -309,11 +326,11 @@ int pcs_radius_search(pcs_stream_t s, const pcs_slot_t *table, int64_t H, const 
   if (n_uf > 0) {
     PCS_LAUNCH(radius_search_kernel<true>, grid, kWarpsPerBlock * 32, 0, as_stream(s), table, (long long)(H - 1),
                (const float4 *)sorted_pts, sorted_idx, g, (const float4 *)queries, (long long)m, order, qr, radius,
-               radius_scalar, K, nbr_idx, nbr_d2, nbr_cnt, uf, skip_full_cnt);
+               radius_scalar, K, nbr_idx, nbr_d2, nbr_cnt, uf, skip_full_cnt, occ, occ_shift);
   } else {
     PCS_LAUNCH(radius_search_kernel<false>, grid, kWarpsPerBlock * 32, 0, as_stream(s), table, (long long)(H - 1),
                (const float4 *)sorted_pts, sorted_idx, g, (const float4 *)queries, (long long)m, order, qr, radius,
-               radius_scalar, K, nbr_idx, nbr_d2, nbr_cnt, uf, skip_full_cnt);
+               radius_scalar, K, nbr_idx, nbr_d2, nbr_cnt, uf, skip_full_cnt, occ, occ_shift);
   }
   return 0;
 }

@@ -4,6 +4,7 @@ torch is used for device memory and the current stream only; every computation o
 in libpcseq_b200.so.  All functions raise on CPU tensors -- there is no fallback.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -12,6 +13,7 @@ from . import _lib
 
 PCS_MAX_K = 32
 PCS_MAX_SEGMENTS = 64
+OCC_BITS_PER_SLOT = int(os.environ.get("PCS_OCC_BITS_PER_SLOT", "16"))  # 0 disables the occupancy bitmap
 
 # Optional per-kernel CUDA-event log (bench.py's roofline leg): name -> list of (start, end, meta)
 _EVENT_LOG = None
@@ -127,11 +129,14 @@ class CellGrid:
             self.sorted_pts = torch.empty(max(self.n, 1), 4, dtype=torch.float32, device=dev)
             self.sorted_idx = torch.empty(max(self.n, 1), dtype=torch.int32, device=dev)
             self.counters = torch.empty(4, dtype=torch.int32, device=dev)
+            # occupancy bitmap: 16 bits per table slot (<= 2^32 bits); empty neighbour cells cost the search one load
+            self.occ_bits = min(max(self.H * OCC_BITS_PER_SLOT, 32), 1 << 32) if OCC_BITS_PER_SLOT > 0 else 0
+            self.occ = torch.empty(self.occ_bits // 32, dtype=torch.int32, device=dev) if self.occ_bits else None
             with _timed("hash_build", n=self.n, H=self.H):
                 _lib.check(L.pcs_hash_build(s, _ptr(self.ref), self.n, self.seg_div, self.n_seg, _ptr(self.seg_lo),
                                             _ptr(self.seg_dims), _f4(self.vs), _ptr(self.table), self.H,
-                                            _ptr(self.sorted_pts), _ptr(self.sorted_idx), _ptr(self.counters)),
-                           "pcs_hash_build")
+                                            _ptr(self.sorted_pts), _ptr(self.sorted_idx), _ptr(self.counters),
+                                            _ptr(self.occ), self.occ_bits), "pcs_hash_build")
 
     def check(self):
         """Synchronising check of the device-side error flag (table full / key overflow)."""
@@ -192,7 +197,8 @@ class CellGrid:
                 _stream(), _ptr(self.table), self.H, _ptr(self.sorted_pts), _ptr(self.sorted_idx), self.seg_div,
                 self.n_seg, _ptr(self.seg_lo), _ptr(self.seg_dims), _f4(self.vs), _ptr(query), m, _ptr(order),
                 _i4(qmin), _i4(qmax), _ptr(rad_t), rad_s, int(K), _ptr(nbr_idx), _ptr(nbr_d2), _ptr(nbr_cnt),
-                uf_ptrs, uf_r2, uf_full, n_uf, _ptr(skip_full_cnt)), "pcs_radius_search")
+                uf_ptrs, uf_r2, uf_full, n_uf, _ptr(skip_full_cnt), _ptr(self.occ), self.occ_bits),
+                "pcs_radius_search")
         return nbr_idx, nbr_cnt, nbr_d2
 
 
