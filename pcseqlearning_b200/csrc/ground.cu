@@ -131,26 +131,47 @@ __device__ __forceinline__ void warp_flush(float *acc10, int &hits, double *dst,
   hits = 0;
 }
 
-// One IRLS iteration of a team (ratios [r0, r0+nr)) over the block's contiguous voxel range [v0, v1).
+// Phase A of an IRLS iteration (all blocks): fit plane `it` of every (active ratio, non-empty super-pillar) once,
+// publish it, and clear the spare accumulators of the pair.  s_act: the active ratio ids.
+__device__ void ransac_fit(const RansacArgs &A, int it, const int *s_act, int n_act) {
+  const long long RC = (long long)A.R * A.C;
+  const int bf = it % 3, bs = (it + 2) % 3;
+  const double *acc_fit = A.acc + (long long)bf * RC * kAcc;
+  double *acc_spare = A.acc + (long long)bs * RC * kAcc;
+  int *nhit_spare = A.nhit + (long long)bs * RC;
+  float *pub_new = A.planes + (long long)(it & 1) * RC * 6;
+  const long long tasks = (long long)n_act * A.C;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < tasks;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(t % A.C), r = s_act[t / A.C];
+    if (A.seg_start[p + 1] <= A.seg_start[p]) continue;  // empty super-pillar
+    const long long rp = (long long)r * A.C + p;
+    PlaneN pl;
+    fit_plane(A, p, acc_fit + rp * kAcc, pl);
+    float *d = pub_new + rp * 6;
+    d[0] = pl.cx; d[1] = pl.cy; d[2] = pl.cz; d[3] = pl.nx; d[4] = pl.ny; d[5] = pl.nz;
+    for (int k = 0; k < kAcc; k++) acc_spare[rp * kAcc + k] = 0.0;
+    nhit_spare[rp] = 0;
+  }
+}
+
+// Phase B of an IRLS iteration of a team (its nr still-active ratios, ids packed 8 bits each in `rids`) over the
+// block's contiguous voxel range [v0, v1).
 //   it < 0  : weights from the height prior, moments of fit 0
-//   it >= 0 : fit plane `it` from acc[bf]; previous plane = prior (it == 0) or planes[(it-1)&1]; evaluate the new
-//             plane (weight, |dw|, hit) and accumulate the moments of fit it+1 into acc[bn].
-// The block that owns a pillar (holds its first voxel) publishes its planes and clears the spare buffers.
-__device__ void ransac_step(const RansacArgs &A, long long v0, long long v1, int it, int r0, int nr, unsigned int done,
+//   it >= 0 : new plane = planes[it & 1] (phase A); previous plane = prior (it == 0) or planes[(it-1) & 1]; evaluate
+//             the new plane (weight, |dw|, hit) and accumulate the moments of fit it+1 into acc[(it+1) % 3].
+__device__ void ransac_step(const RansacArgs &A, long long v0, long long v1, int it, unsigned int rids, int nr,
                             float (*s_new)[kGroup][8], float (*s_old)[kGroup][8], float (*s_org)[3]) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nwarp = kRansacThreads / 32;
   const float sigma = sqrtf(A.sigma2);
   const long long RC = (long long)A.R * A.C;
-  const int bf = ((it % 3) + 3) % 3, bn = (it + 1) % 3, bs = (it + 2) % 3;
+  const int bn = (it + 1) % 3;
   const bool first = it < 0;
-  double *acc_fit = A.acc + (long long)bf * RC * kAcc;
   double *acc_next = A.acc + (long long)(first ? 0 : bn) * RC * kAcc;
-  double *acc_spare = A.acc + (long long)(first ? 2 : bs) * RC * kAcc;
   int *nhit_next = A.nhit + (long long)(first ? 0 : bn) * RC;
-  int *nhit_spare = A.nhit + (long long)(first ? 2 : bs) * RC;
   unsigned int *gmax_next = A.gmax + (first ? 0 : bn) * A.R;
-  float *pub_new = A.planes + (long long)(it & 1) * RC * 6;
+  const float *pub_new = A.planes + (long long)(it & 1) * RC * 6;
   const float *pub_old = A.planes + (long long)((it - 1) & 1) * RC * 6;
   float dmax[kG];
 #pragma unroll
@@ -161,37 +182,23 @@ __device__ void ransac_step(const RansacArgs &A, long long v0, long long v1, int
     for (int g0 = p_first; g0 <= p_last; g0 += kGroup) {
       const int g1 = min(g0 + kGroup, p_last + 1);  // pillars [g0, g1)
       __syncthreads();
-      for (int t = threadIdx.x; t < (g1 - g0) * nr; t += kRansacThreads) {
-        const int p = g0 + t / nr, g = t % nr, r = r0 + g;
+      for (int t = threadIdx.x; t < (g1 - g0) * 3; t += kRansacThreads)
+        s_org[t / 3][t % 3] = A.origin[(long long)g0 * 3 + t];
+      // planes of the group from global memory (written in phase A, before the grid barrier): plain loads
+      for (int t = threadIdx.x; t < (g1 - g0) * nr * 6; t += kRansacThreads) {
+        const int k = t % 6, lp = (t / 6) % (g1 - g0), g = t / (6 * (g1 - g0));
+        const int p = g0 + lp, r = (rids >> (8 * g)) & 0xffu;
         const long long rp = (long long)r * A.C + p;
-        if (g == 0) {
-          s_org[p - g0][0] = A.origin[p * 3 + 0];
-          s_org[p - g0][1] = A.origin[p * 3 + 1];
-          s_org[p - g0][2] = A.origin[p * 3 + 2];
-        }
-        if ((done >> r) & 1u) continue;
-        const long long ps = A.seg_start[p];
-        const bool owner = ps >= v0 && ps < v1 && A.seg_start[p + 1] > ps;
         if (first) {
-          // "plane" of the prior: only its height is used
-          s_new[g][p - g0][0] = A.cmin_z[p] * A.ratios[r] + A.cmax_z[p] * (1.0f - A.ratios[r]);  // :148
+          // "plane" of the prior: only its height is used (:148)
+          if (k == 0) s_new[g][lp][0] = A.cmin_z[p] * A.ratios[r] + A.cmax_z[p] * (1.0f - A.ratios[r]);
         } else {
-          PlaneN pl;
-          fit_plane(A, p, acc_fit + rp * kAcc, pl);
-          float *d = s_new[g][p - g0];
-          d[0] = pl.cx; d[1] = pl.cy; d[2] = pl.cz; d[3] = pl.nx; d[4] = pl.ny; d[5] = pl.nz;
-          float *o = s_old[g][p - g0];
+          s_new[g][lp][k] = __ldcg(pub_new + rp * 6 + k);
           if (it == 0) {
-            o[0] = A.cmin_z[p] * A.ratios[r] + A.cmax_z[p] * (1.0f - A.ratios[r]);
+            if (k == 0) s_old[g][lp][0] = A.cmin_z[p] * A.ratios[r] + A.cmax_z[p] * (1.0f - A.ratios[r]);
           } else {
-            for (int k = 0; k < 6; k++) o[k] = pub_old[rp * 6 + k];
+            s_old[g][lp][k] = __ldcg(pub_old + rp * 6 + k);
           }
-          if (owner)
-            for (int k = 0; k < 6; k++) pub_new[rp * 6 + k] = d[k];
-        }
-        if (owner) {
-          for (int k = 0; k < kAcc; k++) acc_spare[rp * kAcc + k] = 0.0;
-          nhit_spare[rp] = 0;
         }
       }
       __syncthreads();
@@ -221,18 +228,18 @@ __device__ void ransac_step(const RansacArgs &A, long long v0, long long v1, int
           if (cur >= 0) {
 #pragma unroll
             for (int g = 0; g < kG; g++)
-              if (g < nr && !((done >> (r0 + g)) & 1u))
-                warp_flush(acc[g], hits[g], acc_next + ((long long)(r0 + g) * A.C + cur) * kAcc,
-                           nhit_next + (long long)(r0 + g) * A.C + cur, lane);
+              if (g < nr)
+                warp_flush(acc[g], hits[g], acc_next + ((long long)((rids >> (8 * g)) & 0xffu) * A.C + cur) * kAcc,
+                           nhit_next + (long long)((rids >> (8 * g)) & 0xffu) * A.C + cur, lane);
           }
           cur = pl0;
         }
         if (!uniform && cur >= 0) {
 #pragma unroll
           for (int g = 0; g < kG; g++)
-            if (g < nr && !((done >> (r0 + g)) & 1u))
-              warp_flush(acc[g], hits[g], acc_next + ((long long)(r0 + g) * A.C + cur) * kAcc,
-                         nhit_next + (long long)(r0 + g) * A.C + cur, lane);
+            if (g < nr)
+              warp_flush(acc[g], hits[g], acc_next + ((long long)((rids >> (8 * g)) & 0xffu) * A.C + cur) * kAcc,
+                         nhit_next + (long long)((rids >> (8 * g)) & 0xffu) * A.C + cur, lane);
           cur = -1;
         }
         if (valid) {
@@ -240,7 +247,7 @@ __device__ void ransac_step(const RansacArgs &A, long long v0, long long v1, int
           const float xr = p.y - s_org[lp][0], yr = p.z - s_org[lp][1], zr = p.w - s_org[lp][2];
 #pragma unroll
           for (int g = 0; g < kG; g++) {
-            if (g >= nr || ((done >> (r0 + g)) & 1u)) continue;
+            if (g >= nr) continue;
             float wnew;
             int hit = 0;
             if (first) {
@@ -284,7 +291,8 @@ __device__ void ransac_step(const RansacArgs &A, long long v0, long long v1, int
               hits[g] += hit;
             } else {  // a pillar boundary inside this warp step: per-lane atomics
               const double w = wnew, x = xr, y = yr, z = zr;
-              double *d = acc_next + ((long long)(r0 + g) * A.C + pid) * kAcc;
+              const long long rg = (rids >> (8 * g)) & 0xffu;
+              double *d = acc_next + (rg * A.C + pid) * kAcc;
               atomicAdd(d + 0, w);
               atomicAdd(d + 1, w * x);
               atomicAdd(d + 2, w * y);
@@ -295,7 +303,7 @@ __device__ void ransac_step(const RansacArgs &A, long long v0, long long v1, int
               atomicAdd(d + 7, w * y * y);
               atomicAdd(d + 8, w * y * z);
               atomicAdd(d + 9, w * z * z);
-              if (hit) atomicAdd(nhit_next + (long long)(r0 + g) * A.C + pid, 1);
+              if (hit) atomicAdd(nhit_next + rg * A.C + pid, 1);
             }
           }
         }
@@ -308,9 +316,9 @@ __device__ void ransac_step(const RansacArgs &A, long long v0, long long v1, int
       if (cur >= 0) {
 #pragma unroll
         for (int g = 0; g < kG; g++)
-          if (g < nr && !((done >> (r0 + g)) & 1u))
-            warp_flush(acc[g], hits[g], acc_next + ((long long)(r0 + g) * A.C + cur) * kAcc,
-                       nhit_next + (long long)(r0 + g) * A.C + cur, lane);
+          if (g < nr)
+            warp_flush(acc[g], hits[g], acc_next + ((long long)((rids >> (8 * g)) & 0xffu) * A.C + cur) * kAcc,
+                       nhit_next + (long long)((rids >> (8 * g)) & 0xffu) * A.C + cur, lane);
       }
     }
   }
@@ -319,36 +327,167 @@ __device__ void ransac_step(const RansacArgs &A, long long v0, long long v1, int
     float d = dmax[g];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) d = fmaxf(d, __shfl_xor_sync(0xffffffffu, d, o));
-    if (lane == 0 && d > 0.f && g < nr) atomicMax(gmax_next + r0 + g, __float_as_uint(d));
+    if (lane == 0 && d > 0.f && g < nr) atomicMax(gmax_next + ((rids >> (8 * g)) & 0xffu), __float_as_uint(d));
   }
 }
+
+#ifdef PCS_RANSAC_TRACE
+// debug build only (tools/trace_ransac.py): per-block timestamps of one IRLS iteration
+__device__ unsigned long long g_ransac_trace[2048 * 4];
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ unsigned int smid() {
+  unsigned int r;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
+  return r;
+}
+#endif
+
+// Adaptive load balance of the voxel sweep.  The cost of a voxel range depends on how many super-pillar boundaries
+// it holds (sparse far-field ranges are several times more expensive per voxel than dense ones), so every block
+// times its sweep and the team re-cuts its ranges so that, assuming a uniform cost density inside each old range,
+// all blocks would have taken the same time.  Scratch lives in static device arrays (one cooperative launch owns
+// the GPU at a time); only the order of the atomic additions depends on the cut.
+constexpr int kMaxRansacGrid = 2048;
+__device__ unsigned int g_bal_dur[kMaxRansacGrid];
+__device__ long long g_bal_v0[kMaxRansacGrid];
 
 __global__ void __launch_bounds__(kRansacThreads, 3) ground_ransac_kernel(RansacArgs A) {
   cg::grid_group grid = cg::this_grid();
   __shared__ __align__(16) float s_new[kG][kGroup][8];
   __shared__ __align__(16) float s_old[kG][kGroup][8];
   __shared__ float s_org[kGroup][3];
-  // teams of blocks: team t iterates ratios [t*kG, t*kG + kG); inside a team every block owns a contiguous,
-  // 32-aligned voxel range
-  const int n_teams = (A.R + kG - 1) / kG;
-  const int bpt = gridDim.x / n_teams;  // blocks per team (grid is a multiple of n_teams)
-  const int team = blockIdx.x / bpt, brank = blockIdx.x % bpt;
-  const int r0 = team * kG, nr = min(kG, A.R - r0);
-  const long long per = (((A.Nv + bpt - 1) / bpt) + 31) / 32 * 32;
-  const long long v0 = min((long long)brank * per, A.Nv), v1 = min(v0 + per, A.Nv);
+  __shared__ int s_act[kMaxRatios];  // ids of the still-active ratios
+  __shared__ int s_nact;
+  __shared__ long long s_cut[2];
+  // Teams of blocks: every iteration the still-active ratios are dealt out to ceil(n_active / kG) teams (sizes
+  // differ by at most one) and every team gets a share of the grid proportional to its ratio count, so the SMs of
+  // ratios that have converged go to the ones still iterating.  Inside a team every block owns a contiguous,
+  // 32-aligned voxel range.  The assignment only depends on `done`, which every thread derives identically.
   const unsigned int all_done = (A.R >= 32) ? 0xffffffffu : ((1u << A.R) - 1u);
   unsigned int done = 0;
+  unsigned int rids = 0;
+  int nr = 0;
+  long long v0 = 0, v1 = 0;
+  int tb0 = 0, tb1 = 0;  // blocks of my team
+  auto assign = [&]() {
+    const unsigned int act = all_done & ~done;
+    const int n_act = __popc(act);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int k = 0;
+      for (unsigned int m = act; m; m &= m - 1) s_act[k++] = __ffs(m) - 1;
+      s_nact = k;
+    }
+    __syncthreads();
+    nr = 0;
+    rids = 0;
+    v0 = v1 = 0;
+    if (n_act == 0) return;
+    const int n_teams = (n_act + kG - 1) / kG;
+    const int base = n_act / n_teams, rem = n_act % n_teams;
+    int first_r = 0;  // index (among active ratios) of the team's first ratio
+    for (int t = 0; t < n_teams; t++) {
+      const int sz = base + (t < rem ? 1 : 0);
+      const int b0 = (int)((long long)gridDim.x * first_r / n_act);
+      const int b1 = (int)((long long)gridDim.x * (first_r + sz) / n_act);
+      if ((int)blockIdx.x >= b0 && (int)blockIdx.x < b1) {
+        nr = sz;
+        unsigned int m = act;
+        for (int k = 0; k < first_r; k++) m &= m - 1;  // skip the ratios of earlier teams
+        for (int g = 0; g < sz; g++) {
+          rids |= (unsigned int)(__ffs(m) - 1) << (8 * g);
+          m &= m - 1;
+        }
+        const int bpt = b1 - b0, brank = (int)blockIdx.x - b0;
+        tb0 = b0;
+        tb1 = b1;
+        const long long per = (((A.Nv + bpt - 1) / bpt) + 31) / 32 * 32;
+        v0 = min((long long)brank * per, A.Nv);
+        v1 = min(v0 + per, A.Nv);
+        return;
+      }
+      first_r += sz;
+    }
+  };
 
-  ransac_step(A, v0, v1, -1, r0, nr, done, s_new, s_old, s_org);
+  // new cut of the team's ranges from the sweep times of the last iteration (every block derives its two cut
+  // points with the same arithmetic as its neighbours)
+  auto rebalance = [&]() {
+    if (threadIdx.x == 0) {
+      const int bpt = tb1 - tb0, brank = (int)blockIdx.x - tb0;
+      double total = 0.0;
+      for (int j = tb0; j < tb1; j++) total += (double)__ldcg(&g_bal_dur[j]);
+      for (int e = 0; e < 2; e++) {
+        const int k = brank + e;
+        long long v = (k >= bpt) ? A.Nv : 0;
+        if (k > 0 && k < bpt) {
+          const double target = total * (double)k / (double)bpt;
+          double cum = 0.0;
+          int j = tb0;
+          for (; j < tb1; j++) {
+            const double d = (double)__ldcg(&g_bal_dur[j]);
+            if (cum + d >= target) break;
+            cum += d;
+          }
+          if (j >= tb1) {
+            v = A.Nv;
+          } else {
+            const long long a = __ldcg(&g_bal_v0[j]);
+            const long long b = (j + 1 < tb1) ? __ldcg(&g_bal_v0[j + 1]) : A.Nv;
+            const double d = (double)__ldcg(&g_bal_dur[j]);
+            const double frac = d > 0.0 ? (target - cum) / d : 0.0;
+            v = a + (long long)(frac * (double)(b - a));
+            v = (v + 16) / 32 * 32;
+            v = max(a, min(v, b));
+          }
+        }
+        s_cut[e] = min(v, A.Nv);
+      }
+    }
+    __syncthreads();
+    v0 = s_cut[0];
+    v1 = s_cut[1];
+    __syncthreads();
+  };
+
+  assign();
+  ransac_step(A, v0, v1, -1, rids, nr, s_new, s_old, s_org);
   grid.sync();
   int it = 0;
   for (; it < A.max_iter && done != all_done; it++) {
     const int bn = (it + 1) % 3, bs = (it + 2) % 3;
     if (blockIdx.x == 0)
       for (int r = threadIdx.x; r < A.R; r += kRansacThreads) A.gmax[bs * A.R + r] = 0u;
-    ransac_step(A, v0, v1, it, r0, nr, done, s_new, s_old, s_org);
+    ransac_fit(A, it, s_act, s_nact);
     grid.sync();
+#ifdef PCS_RANSAC_TRACE
+    if (it == 20 && threadIdx.x == 0 && blockIdx.x < 2048) g_ransac_trace[blockIdx.x * 4 + 0] = gtimer();
+#endif
+    const long long t_sweep = clock64();
+    if (nr > 0) ransac_step(A, v0, v1, it, rids, nr, s_new, s_old, s_org);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const long long dt = clock64() - t_sweep;
+      g_bal_dur[blockIdx.x] = (unsigned int)min(dt, 0xffffffffLL);
+      g_bal_v0[blockIdx.x] = v0;
+    }
+#ifdef PCS_RANSAC_TRACE
+    __syncthreads();
+    if (it == 20 && threadIdx.x == 0 && blockIdx.x < 2048) {
+      g_ransac_trace[blockIdx.x * 4 + 1] = gtimer();
+      g_ransac_trace[blockIdx.x * 4 + 2] = ((unsigned long long)smid() << 32) | (unsigned int)nr;
+    }
+#endif
+    grid.sync();
+#ifdef PCS_RANSAC_TRACE
+    if (it == 20 && threadIdx.x == 0 && blockIdx.x < 2048) g_ransac_trace[blockIdx.x * 4 + 3] = gtimer();
+#endif
     // per-ratio stopping rule (preprocessor_utils.py:76-78), evaluated identically by every thread
+    const unsigned int before = done;
     for (int r = 0; r < A.R; r++) {
       if ((done >> r) & 1u) continue;
       const bool conv = __uint_as_float(A.gmax[bn * A.R + r]) < A.stopping_delta;
@@ -361,10 +500,19 @@ __global__ void __launch_bounds__(kRansacThreads, 3) ground_ransac_kernel(Ransac
         }
       }
     }
+    if (done != before)
+      assign();  // new teams: back to the even cut
+    else if (nr > 0 && (it < 4 || (it & (it - 1)) == 0))
+      rebalance();
   }
   grid.sync();
   // owners (team 0) keep, ratio after ratio, the plane that explains the most voxels (:160-170)
-  if (team == 0 && v1 > v0) {
+  {
+    const long long per = (((A.Nv + gridDim.x - 1) / gridDim.x) + 31) / 32 * 32;
+    v0 = min((long long)blockIdx.x * per, A.Nv);
+    v1 = min(v0 + per, A.Nv);
+  }
+  if (v1 > v0) {
     const long long RC = (long long)A.R * A.C;
     const int p_first = A.cidx[v0], p_last = A.cidx[v1 - 1];
     for (int p = p_first + threadIdx.x; p <= p_last; p += kRansacThreads) {
@@ -605,6 +753,8 @@ int pcs_ground_ransac(pcs_stream_t s, const float *vox, const int32_t *cidx, con
   if (bpt > cap) bpt = cap;
   if (bpt < 1) bpt = 1;
   long long blocks = bpt * n_teams;
+  if (blocks < n_ratios) blocks = n_ratios;  // the in-kernel team assignment needs one block per active ratio
+  if (blocks > kMaxRansacGrid) blocks = kMaxRansacGrid;
   void *args[] = {&A};
   cudaError_t e = cudaLaunchCooperativeKernel((void *)ground_ransac_kernel, dim3((unsigned)blocks),
                                               dim3(kRansacThreads), args, 0, as_stream(s));
@@ -612,6 +762,12 @@ int pcs_ground_ransac(pcs_stream_t s, const float *vox, const int32_t *cidx, con
   if (e != cudaSuccess) return set_error((int)e, "ground_ransac_kernel (cooperative launch)");
   return check_launch("ground_ransac_kernel");
 }
+
+#ifdef PCS_RANSAC_TRACE
+int pcs_debug_ransac_trace(unsigned long long *host_out) {
+  return (int)cudaMemcpyFromSymbol(host_out, g_ransac_trace, sizeof(unsigned long long) * 2048 * 4);
+}
+#endif
 
 int pcs_l1_heightfield(pcs_stream_t s, const float *min_z, const float *weight, float *h, float *m, float *v, int X,
                        int Y, float lr, float lr_gamma, int decay_step, float rigid_weight, int max_iters,
