@@ -176,6 +176,7 @@ def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     from pcseqlearning_b200 import ops
+    from pcseqlearning_b200.data_staging import DevicePrefetcher
     from pcseqlearning_b200.synthetic import generate_sequence
 
     torch.cuda.set_device(local_rank)
@@ -203,14 +204,25 @@ def run_ours(args, rank, world, local_rank):
         model(batch)
         return model.forward_dict["sequences"][0]
 
-    def step_e2e():
-        b = dict(batch)
-        for k in POINT_KEYS:
-            b[k] = host[k].to(dev, non_blocking=True)
-        model(b)
-        seq = model.forward_dict["sequences"][0]
-        out = torch.stack([seq["num_component_rad1x25"].sum(), seq["num_component_rad0x75"].sum(),
-                           seq["num_component_rad0x25"].sum()]).cpu()  # device -> host read of the result
+    def result_of(seq):
+        return torch.stack([seq["num_component_rad1x25"].sum(), seq["num_component_rad0x75"].sum(),
+                            seq["num_component_rad0x25"].sum()]).cpu()  # device -> host read of the result
+
+    def host_batches(n):
+        for _ in range(n):
+            b = dict(batch)
+            b.update(host)  # the per-point inputs start in pinned host memory every step
+            yield b
+
+    def run_e2e(steps):
+        """The user-facing loop: DevicePrefetcher (copy of batch k+1 overlaps the processing of batch k) ->
+        SimpleReg.forward -> result read back on the host.  All `steps` H2D copies happen inside the loop."""
+        seq = out = None
+        for b in DevicePrefetcher(host_batches(steps), dev):
+            seq = out = None
+            model(b)
+            seq = model.forward_dict["sequences"][0]
+            out = result_of(seq)
         return seq, out
 
     def barrier():
@@ -271,8 +283,8 @@ def run_ours(args, rank, world, local_rank):
     launches = ops.launch_count()
     log = ops.event_log()
     ops.enable_event_log(False)
-    step_e2e()
-    ms_e2e, (seq_e, out_e) = timed(step_e2e, args.steps)
+    run_e2e(2)
+    ms_e2e, (seq_e, out_e) = timed(lambda: run_e2e(args.steps), 1)
     clocks = sampler.summary()
 
     # roofline of the dominant kernel (radius search): algorithmic bytes per launch / mean launch duration
@@ -304,7 +316,9 @@ def run_ours(args, rank, world, local_rank):
                    "parallelism": "replicas" if world > 1 else "single", "generate_s": round(gen_s, 1)},
         "e2e": {"value": round(e2e, 3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": int(out_e.numel() * out_e.element_size()),
-                "ms_per_step": round(ms_e2e / args.steps, 3)},
+                "ms_per_step": round(ms_e2e / args.steps, 3),
+                "pipeline": "pinned host batch -> DevicePrefetcher (copy of step k+1 overlaps step k) -> "
+                            "SimpleReg.forward -> .cpu() of the component counts"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "radius_search_kernel<fused union-find>", "achieved": round(achieved, 2),
                      "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": round(achieved / peak, 5),

@@ -100,6 +100,12 @@ __device__ __noinline__ void fit_plane(const RansacArgs &A, int p, const double 
   pl.nz = nrm[2];
 }
 
+__device__ __forceinline__ float fast_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 // IRLS weight of a voxel for a plane (preprocessor_utils.py:72-75); err returned for the hit test.
 // One fast reciprocal for both factors: sigma2 * 0.25 / ((err^2 + sigma2) (|d|^2 + 0.25)); the weights feed a
 // tolerance-compared fit, and the previous weight is recomputed with the same expression (bit-identical).
@@ -107,12 +113,12 @@ __device__ __forceinline__ float plane_weight(const PlaneN &pl, float x, float y
   const float dx = x - pl.cx, dy = y - pl.cy, dz = z - pl.cz;
   err = fabsf(dx * pl.nx + dy * pl.ny + dz * pl.nz);
   const float den = (err * err + sigma2) * (dx * dx + dy * dy + dz * dz + 0.25f);
-  return __fdividef(sigma2 * 0.25f, den);
+  return sigma2 * 0.25f * fast_rcp(den);  // den >= sigma2 / 4 > 0: no range fix-up needed
 }
 
 __device__ __forceinline__ float prior_weight(float prior_z, float z, float sigma2) {
   const float zd = prior_z - z;
-  return __fdividef(sigma2, zd * zd + sigma2);
+  return sigma2 * fast_rcp(zd * zd + sigma2);
 }
 
 __device__ __forceinline__ void warp_flush(float *acc10, int &hits, double *dst, int *hit_dst, int lane) {
@@ -242,14 +248,30 @@ __device__ void ransac_step(const RansacArgs &A, long long v0, long long v1, int
                          nhit_next + (long long)((rids >> (8 * g)) & 0xffu) * A.C + cur, lane);
           cur = -1;
         }
+        // segments of equal super-pillar id inside this warp step (ids ascend, so segments are lane ranges):
+        // only needed when the step is not uniform
+        int seg_end = 32;
+        bool seg_head = false;
+        if (!uniform) {
+          const int pid_prev = __shfl_up_sync(0xffffffffu, pid, 1);
+          seg_head = lane == 0 || pid != pid_prev;
+          const unsigned int heads = __ballot_sync(0xffffffffu, seg_head);
+          const unsigned int above = heads & ~((2u << lane) - 1u);
+          seg_end = above ? __ffs(above) - 1 : 32;
+        }
+        const int lp = valid ? pid - g0 : 0;
+        float xr = 0.f, yr = 0.f, zr = 0.f;
         if (valid) {
-          const int lp = pid - g0;
-          const float xr = p.y - s_org[lp][0], yr = p.z - s_org[lp][1], zr = p.w - s_org[lp][2];
+          xr = p.y - s_org[lp][0];
+          yr = p.z - s_org[lp][1];
+          zr = p.w - s_org[lp][2];
+        }
 #pragma unroll
-          for (int g = 0; g < kG; g++) {
-            if (g >= nr) continue;
-            float wnew;
-            int hit = 0;
+        for (int g = 0; g < kG; g++) {
+          if (g >= nr) continue;
+          float wnew = 0.f;
+          int hit = 0;
+          if (valid) {
             if (first) {
               wnew = prior_weight(s_new[g][lp][0], p.w, A.sigma2);
             } else {
@@ -276,34 +298,41 @@ __device__ void ransac_step(const RansacArgs &A, long long v0, long long v1, int
                 dmax[g] = fmaxf(dmax[g], fabsf(wnew - wold));
               }
             }
-            if (uniform) {
-              const float wx = wnew * xr, wy = wnew * yr, wz = wnew * zr;
-              acc[g][0] += wnew;
-              acc[g][1] += wx;
-              acc[g][2] += wy;
-              acc[g][3] += wz;
-              acc[g][4] += wx * xr;
-              acc[g][5] += wx * yr;
-              acc[g][6] += wx * zr;
-              acc[g][7] += wy * yr;
-              acc[g][8] += wy * zr;
-              acc[g][9] += wz * zr;
-              hits[g] += hit;
-            } else {  // a pillar boundary inside this warp step: per-lane atomics
-              const double w = wnew, x = xr, y = yr, z = zr;
+          }
+          const float wx = wnew * xr, wy = wnew * yr, wz = wnew * zr;
+          if (uniform) {  // invalid lanes add zeros
+            acc[g][0] += wnew;
+            acc[g][1] += wx;
+            acc[g][2] += wy;
+            acc[g][3] += wz;
+            acc[g][4] += wx * xr;
+            acc[g][5] += wx * yr;
+            acc[g][6] += wx * zr;
+            acc[g][7] += wy * yr;
+            acc[g][8] += wy * zr;
+            acc[g][9] += wz * zr;
+            hits[g] += hit;
+          } else {
+            // a super-pillar boundary inside this warp step: segmented sums, one set of atomics per segment
+            float m[kAcc] = {wnew, wx, wy, wz, wx * xr, wx * yr, wx * zr, wy * yr, wy * zr, wz * zr};
+            int h = hit;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+              const bool take = lane + o < seg_end;
+#pragma unroll
+              for (int k = 0; k < kAcc; k++) {
+                const float t = __shfl_down_sync(0xffffffffu, m[k], o);
+                if (take) m[k] += t;
+              }
+              const int th = __shfl_down_sync(0xffffffffu, h, o);
+              if (take) h += th;
+            }
+            if (seg_head && valid) {
               const long long rg = (rids >> (8 * g)) & 0xffu;
               double *d = acc_next + (rg * A.C + pid) * kAcc;
-              atomicAdd(d + 0, w);
-              atomicAdd(d + 1, w * x);
-              atomicAdd(d + 2, w * y);
-              atomicAdd(d + 3, w * z);
-              atomicAdd(d + 4, w * x * x);
-              atomicAdd(d + 5, w * x * y);
-              atomicAdd(d + 6, w * x * z);
-              atomicAdd(d + 7, w * y * y);
-              atomicAdd(d + 8, w * y * z);
-              atomicAdd(d + 9, w * z * z);
-              if (hit) atomicAdd(nhit_next + rg * A.C + pid, 1);
+#pragma unroll
+              for (int k = 0; k < kAcc; k++) atomicAdd(d + k, (double)m[k]);
+              if (h) atomicAdd(nhit_next + rg * A.C + pid, h);
             }
           }
         }

@@ -81,3 +81,25 @@ def test_tracking_follows_moving_vehicle(pipeline_run):
     assert ex["fxyz"].shape[0] > 0
     frames = ex["fxyz"][:, 0].round().long()
     assert int(frames.max()) >= 6, "no component was tracked for MIN_MOVE_FRAME frames"
+
+
+@pytest.mark.gpu
+def test_device_prefetcher_roundtrip():
+    """DevicePrefetcher / load_data_to_gpu (reference: pcdet/models/__init__.py:44-56): same values, same key rules."""
+    import numpy as np
+    from pcseqlearning_b200.data_staging import DevicePrefetcher, load_data_to_gpu
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(0)
+    host = [dict(point_bxyz=torch.from_numpy(rng.standard_normal((1000 + i, 4)).astype(np.float32)).pin_memory(),
+                 point_sweep=rng.integers(0, 5, (1000 + i, 1)), frame_id=np.array(["a", "b"]),
+                 obj_ids=np.arange(3), batch_size=1) for i in range(4)]
+    got = list(DevicePrefetcher(iter(host), dev))
+    assert len(got) == 4
+    for h, g in zip(host, got):
+        assert g["point_bxyz"].is_cuda and torch.equal(g["point_bxyz"].cpu(), h["point_bxyz"])
+        assert g["point_sweep"].is_cuda and np.array_equal(g["point_sweep"].cpu().numpy(), h["point_sweep"])
+        assert isinstance(g["frame_id"], np.ndarray) and isinstance(g["obj_ids"], np.ndarray)  # skipped keys
+        assert g["batch_size"] == 1
+        assert not h["point_bxyz"].is_cuda  # the host batch is left untouched
+    b = load_data_to_gpu(dict(host[0]), dev)
+    assert b["point_bxyz"].is_cuda
