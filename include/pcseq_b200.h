@@ -143,24 +143,27 @@ int pcs_point_segments(pcs_stream_t s, const float *pts, int64_t n, int seg_div,
  *   bounds   uint32[8] from pcs_bounds_* with n_seg = 1
  *   size     (host) float[4] = [1, gx, gy, gz]
  *   start    float[4] (device), strides int64[5] (device; [4] = cells of the bounding grid)
- *   table    16-byte slots [H] (H power of two, cleared by the call), pt_slot int32[n]
- *   sums     optional double[H][4] (per-slot fp64 sums), maxidx optional int32[H]
- *   ukeys / uslots  int64[n] / int32[n]: unique keys and their slots in claim order;
+ *   table    16-byte slots [H] (H power of two >= n, cleared by the call): cell key -> dense voxel id
+ *   pt_vid   int32[n] dense voxel id (claim order) of every point
+ *   sums     optional double[n][4], maxidx optional int32[n], counts int32[n]: rows indexed by dense id; only
+ *            the first V rows are touched (the claimer of an id initialises them, no pre-clearing needed)
+ *   ukeys / uids  int64[n] / int32[n]: unique keys and their dense ids in claim order (uids[i] = i)
  *   counters int32[4]: [0] = V (number of voxels), [2] = error flag
- * pcs_sort_pairs sorts the V unique (key, slot) pairs by key (radix sort);
- * pcs_voxelize_finish numbers voxels by ascending key and writes inv int64[n], sampled float4[V]
- * (mean of all four columns), maxidx_out int64[V], counts_out int32[V] (any may be NULL). */
+ * pcs_sort_pairs sorts the V unique (key, id) pairs by key (radix sort);
+ * pcs_voxelize_finish numbers voxels by ascending key (rank_of int32[V] scratch: dense id -> rank) and writes
+ * inv int64[n], sampled float4[V] (mean of all four columns), maxidx_out int64[V], counts_out int32[V]
+ * (any of the outputs may be NULL). */
 int pcs_voxelize_params(pcs_stream_t s, const uint32_t *bounds, const float *size, int ignore_dim0, float *start,
                         int64_t *strides);
 int pcs_voxelize_insert(pcs_stream_t s, const float *pts, int64_t n, const float *start, const int64_t *strides,
-                        const float *size, int ignore_dim0, void *table, int64_t H, int32_t *pt_slot, double *sums,
-                        int32_t *maxidx, int64_t *ukeys, int32_t *uslots, int32_t *counters);
+                        const float *size, int ignore_dim0, void *table, int64_t H, int32_t *pt_vid, double *sums,
+                        int32_t *maxidx, int32_t *counts, int64_t *ukeys, int32_t *uids, int32_t *counters);
 int64_t pcs_sort_pairs_tmp_bytes(int64_t n);
 int pcs_sort_pairs(pcs_stream_t s, const int64_t *keys_in, int64_t *keys_out, const int32_t *vals_in,
                    int32_t *vals_out, int64_t n, void *tmp, int64_t tmp_bytes);
-int pcs_voxelize_finish(pcs_stream_t s, void *table, int64_t H, const int32_t *uslots_sorted, int64_t V,
-                        const int32_t *pt_slot, int64_t n, const double *sums, const int32_t *maxidx, int64_t *inv,
-                        float *sampled, int64_t *maxidx_out, int32_t *counts_out);
+int pcs_voxelize_finish(pcs_stream_t s, const int32_t *ids_sorted, int64_t V, const int32_t *pt_vid, int64_t n,
+                        const double *sums, const int32_t *maxidx, const int32_t *counts, int32_t *rank_of,
+                        int64_t *inv, float *sampled, int64_t *maxidx_out, int32_t *counts_out);
 /* Upper median per group (rank deg/2 of the sorted values; empty groups -> -1e10).  offsets int64[V+1]
  * = exclusive scan of the group sizes, cursor int32[V] zero-filled scratch, rows int32[n] scratch. */
 int pcs_group_median(pcs_stream_t s, const int64_t *values, const int64_t *inv, int64_t n, const int64_t *offsets,

@@ -42,10 +42,10 @@ _SIGNATURES = {
     "pcs_point_segments": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
     "pcs_voxelize_params": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "pcs_voxelize_insert": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
-                                    c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                    c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pcs_sort_pairs_tmp_bytes": (c_int64, [c_int64]),
     "pcs_sort_pairs": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64]),
-    "pcs_voxelize_finish": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
+    "pcs_voxelize_finish": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pcs_ground_ransac": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_int64, c_int, c_int, c_float, c_float, c_int, c_void_p, c_void_p, c_void_p,

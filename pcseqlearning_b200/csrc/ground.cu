@@ -844,88 +844,120 @@ constexpr int kPruneThreads = 64;
 constexpr int kPruneMaxK = 16;
 constexpr int kPruneMaxN = 8192;
 
+// one selection pass of the warp over the centres: smallest (d2 bits, index) pair greater than (last_d, last_j),
+// optionally restricted to active centres.  Returns index (0x7fffffff if none) and its d2 bits in wd.
+__device__ __forceinline__ int prune_next_nearest(const float *sx, const float *sy, const float *sz, const int *active,
+                                                  int n, float xi, float yi, float zi, unsigned int last_d, int last_j,
+                                                  int lane, unsigned int &wd) {
+  unsigned int bd = 0xffffffffu;
+  int bj = 0x7fffffff;
+  for (int j = lane; j < n; j += 32) {
+    if (active && !active[j]) continue;
+    const float dx = sx[j] - xi, dy = sy[j] - yi, dz = sz[j] - zi;
+    const unsigned int db = __float_as_uint(dx * dx + dy * dy + dz * dz);
+    const bool after = db > last_d || (db == last_d && j > last_j);
+    if (after && (db < bd || (db == bd && j < bj))) {
+      bd = db;
+      bj = j;
+    }
+  }
+  wd = __reduce_min_sync(0xffffffffu, bd);
+  return __reduce_min_sync(0xffffffffu, bd == wd ? bj : 0x7fffffff);
+}
+
+__device__ __forceinline__ float prune_term(const float *sx, const float *sy, const float *sz, int j, float xi, float yi,
+                                            float zi, float nx, float ny, float nz) {
+  const float dx = sx[j] - xi, dy = sy[j] - yi, dz = sz[j] - zi;
+  return fabsf(dx * nx + dy * ny + dz * nz) / (sqrtf(dx * dx + dy * dy + dz * dz) + 1e-4f);
+}
+
 // state (global, zero-initialised by the caller): [0] / [2] max-curvature bits of even / odd evaluation rounds (the
 // slot of the next round is cleared while nobody uses it), [1] removed count.
-// Every thread owns at most one plane (the launch uses ceil(n / 64) <= 128 CTAs).  A plane's curvature only changes
-// when one of its K nearest centres is removed, so after the first round only those "dirty" planes are re-evaluated;
-// a dirty plane is handled by its whole warp: K selection passes over the active centres, each picking the next
-// smallest (d2, index) pair -- the order the reference's knn returns them in.
+// Every warp owns `pw` planes.  For each of them it first builds the list of its 32 nearest centres (sorted by
+// (d2, index), the order the reference's knn returns them in): as long as K of those are still active, the K nearest
+// ACTIVE centres are the first K active entries of the list, so a round costs one ballot per plane instead of a scan
+// over all centres.  A plane that has lost too many of its 32 falls back to the full selection scan.
 __global__ void __launch_bounds__(kPruneThreads) plane_prune_kernel(const float *__restrict__ xyz,
                                                                     const float *__restrict__ normal, int n, int K,
                                                                     const float *__restrict__ thresholds, int n_thr,
                                                                     int *__restrict__ keep, float *__restrict__ curv,
-                                                                    unsigned int *__restrict__ state) {
+                                                                    unsigned int *__restrict__ state, int pw) {
   cg::grid_group grid = cg::this_grid();
-  extern __shared__ float sm[];  // x[n], y[n], z[n], active[n]
-  __shared__ int s_nb[kPruneMaxK][kPruneThreads];  // neighbour lists of this CTA's planes
+  extern __shared__ float sm[];  // x[n], y[n], z[n], active[n], cand[2][pw][32], c[2][pw]
   float *sx = sm, *sy = sm + n, *sz = sm + 2 * n;
   int *active = reinterpret_cast<int *>(sm + 3 * n);
-  const int lane = threadIdx.x & 31;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // my plane
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int *cand = reinterpret_cast<int *>(sm + 4 * n) + warp * pw * 32;
+  float *cq = sm + 4 * n + (kPruneThreads / 32) * pw * 32 + warp * pw;
+  const int first = (blockIdx.x * (kPruneThreads / 32) + warp) * pw;  // my planes: [first, first + pw)
   for (int j = threadIdx.x; j < n; j += blockDim.x) {
     sx[j] = xyz[j * 3 + 0];
     sy[j] = xyz[j * 3 + 1];
     sz[j] = xyz[j * 3 + 2];
     active[j] = 1;
   }
-  if (i < n) keep[i] = 1;
+  for (int q = lane; q < pw; q += 32)
+    if (first + q < n) keep[first + q] = 1;
   __syncthreads();
-  const bool mine = i < n;
-  bool alive = mine, dirty = mine;
-  float c = 0.f;
-  float nx = 0.f, ny = 0.f, nz = 0.f;
-  if (mine) {
-    nx = normal[i * 3 + 0];
-    ny = normal[i * 3 + 1];
-    nz = normal[i * 3 + 2];
+  for (int q = 0; q < pw; q++) {
+    const int i = first + q;
+    if (i >= n) break;
+    const float xi = sx[i], yi = sy[i], zi = sz[i];
+    unsigned int last_d = 0u;
+    int last_j = -1, mine = -1;
+    for (int k = 0; k < 32; k++) {
+      unsigned int wd;
+      const int wj = prune_next_nearest(sx, sy, sz, nullptr, n, xi, yi, zi, last_d, last_j, lane, wd);
+      if (wj == 0x7fffffff) break;  // fewer than 32 centres
+      if (lane == k) mine = wj;
+      last_d = wd;
+      last_j = wj;
+    }
+    cand[q * 32 + lane] = mine;
   }
+  __syncwarp();
   int count = n, round = 0;
   bool changed = true;
   float maxc = 0.f;
   for (int t = 0; t < n_thr; t++) {
     if (count < K) break;  // fewer planes than neighbours (grid-uniform)
     if (changed) {
-      unsigned int todo = __ballot_sync(0xffffffffu, alive && dirty);
-      while (todo) {
-        const int d = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const int pi = __shfl_sync(0xffffffffu, i, d);
-        const float xi = sx[pi], yi = sy[pi], zi = sz[pi];
-        const float pnx = __shfl_sync(0xffffffffu, nx, d), pny = __shfl_sync(0xffffffffu, ny, d),
-                    pnz = __shfl_sync(0xffffffffu, nz, d);
-        unsigned int last_d = 0u;
-        int last_j = -1;  // (d2 bits, index) of the previously selected neighbour
+      float m = 0.f;
+      for (int q = 0; q < pw; q++) {
+        const int i = first + q;
+        if (i >= n) break;
+        if (!active[i]) continue;
+        const float xi = sx[i], yi = sy[i], zi = sz[i];
+        const float nx = normal[i * 3 + 0], ny = normal[i * 3 + 1], nz = normal[i * 3 + 2];
+        const int j = cand[q * 32 + lane];
+        const bool a = j >= 0 && active[j];
+        unsigned int ball = __ballot_sync(0xffffffffu, a);
         float acc = 0.f;
-        for (int k = 0; k < K; k++) {
-          unsigned int bd = 0xffffffffu;
-          int bj = 0x7fffffff;
-          for (int j = lane; j < n; j += 32) {
-            if (!active[j]) continue;
-            const float dx = sx[j] - xi, dy = sy[j] - yi, dz = sz[j] - zi;
-            const unsigned int db = __float_as_uint(dx * dx + dy * dy + dz * dz);
-            const bool after = db > last_d || (db == last_d && j > last_j);
-            if (after && (db < bd || (db == bd && j < bj))) {
-              bd = db;
-              bj = j;
-            }
+        if (__popc(ball) >= K) {
+          const float term = a ? prune_term(sx, sy, sz, j, xi, yi, zi, nx, ny, nz) : 0.f;
+          for (int k = 0; k < K; k++) {  // ascending (d2, index), the summation order of the scan below
+            acc += __shfl_sync(0xffffffffu, term, __ffs(ball) - 1);
+            ball &= ball - 1;
           }
-          const unsigned int wd = __reduce_min_sync(0xffffffffu, bd);
-          const int wj = __reduce_min_sync(0xffffffffu, bd == wd ? bj : 0x7fffffff);
-          last_d = wd;
-          last_j = wj;
-          if (lane == d) s_nb[k][threadIdx.x] = wj;
-          const float dx = sx[wj] - xi, dy = sy[wj] - yi, dz = sz[wj] - zi;
-          acc += fabsf(dx * pnx + dy * pny + dz * pnz) / (sqrtf(dx * dx + dy * dy + dz * dz) + 1e-4f);
+        } else {
+          unsigned int last_d = 0u;
+          int last_j = -1;
+          for (int k = 0; k < K; k++) {
+            unsigned int wd;
+            const int wj = prune_next_nearest(sx, sy, sz, active, n, xi, yi, zi, last_d, last_j, lane, wd);
+            last_d = wd;
+            last_j = wj;
+            acc += prune_term(sx, sy, sz, wj, xi, yi, zi, nx, ny, nz);
+          }
         }
-        if (lane == d) {
-          c = acc / (float)K;
+        const float c = acc / (float)K;
+        if (lane == 0) {
+          cq[q] = c;
           curv[i] = c;
-          dirty = false;
         }
+        m = fmaxf(m, c);
       }
-      float m = alive ? c : 0.f;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      __syncwarp();
       unsigned int *slot = state + ((round & 1) ? 2 : 0);
       if (lane == 0 && m > 0.f) atomicMax(slot, __float_as_uint(m));
       grid.sync();
@@ -936,20 +968,22 @@ __global__ void __launch_bounds__(kPruneThreads) plane_prune_kernel(const float 
     if (thresholds[t] > maxc) continue;  // :186-187; nothing changes, no barrier needed
     // remove every plane whose curvature is not below the threshold (at least the arg-max goes)
     const float thr = thresholds[t];
-    const bool drop = alive && !(c < thr);
-    if (drop) keep[i] = 0;
+    bool drop = false;
+    for (int q = lane; q < pw; q += 32) {
+      const int i = first + q;
+      if (i < n && active[i] && !(cq[q] < thr)) {
+        keep[i] = 0;
+        drop = true;
+      }
+    }
+    // (a lane drops at most one plane per 32 owned; pw <= 32)
     const unsigned int dropped = __ballot_sync(0xffffffffu, drop);
     if (lane == 0 && dropped) atomicAdd(state + 1, (unsigned int)__popc(dropped));
-    if (i == 0) state[(round & 1) ? 2 : 0] = 0u;  // slot of the NEXT evaluation round (idle since two barriers)
+    if (blockIdx.x == 0 && threadIdx.x == 0) state[(round & 1) ? 2 : 0] = 0u;  // slot of the NEXT evaluation round
     grid.sync();
     count = n - (int)__ldcg(state + 1);
     for (int j = threadIdx.x; j < n; j += blockDim.x) active[j] = __ldcg(keep + j);
     __syncthreads();
-    if (mine) {
-      alive = active[i] != 0;
-      if (alive && !dirty)
-        for (int k = 0; k < K; k++) dirty |= !active[s_nb[k][threadIdx.x]];
-    }
     changed = true;
   }
 }
@@ -961,15 +995,18 @@ extern "C" int pcs_plane_prune(pcs_stream_t s, const float *xyz, const float *no
   using namespace pcs;
   if (n < 1 || n > kPruneMaxN || K < 1 || K > kPruneMaxK || !xyz || !normal || !thresholds || !keep || !curv || !state)
     return set_error(PCS_ERR_BAD_ARG, "pcs_plane_prune: bad args (n <= 8192, K <= 16)");  // state: uint32[4]
-  size_t smem = (size_t)n * 4 * sizeof(float);
-  cudaFuncSetAttribute(plane_prune_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  int blocks = (n + kPruneThreads - 1) / kPruneThreads;  // one plane per thread
-  if (blocks > sms) return set_error(PCS_ERR_BAD_ARG, "pcs_plane_prune: more planes than co-resident threads");
+  const int wpb = kPruneThreads / 32;
+  int pw = (n + sms * wpb - 1) / (sms * wpb);  // planes per warp, one CTA per SM at most
+  if (pw < 1) pw = 1;
+  if (pw > 32) return set_error(PCS_ERR_BAD_ARG, "pcs_plane_prune: too many planes for this device");
+  int blocks = (n + pw * wpb - 1) / (pw * wpb);
+  size_t smem = ((size_t)n * 4 + (size_t)wpb * pw * 33) * sizeof(float);
+  cudaFuncSetAttribute(plane_prune_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   void *args[] = {(void *)&xyz, (void *)&normal, (void *)&n, (void *)&K, (void *)&thresholds, (void *)&n_thr,
-                  (void *)&keep, (void *)&curv, (void *)&state};
+                  (void *)&keep, (void *)&curv, (void *)&state, (void *)&pw};
   cudaError_t e = cudaLaunchCooperativeKernel((void *)plane_prune_kernel, dim3(blocks), dim3(kPruneThreads), args, smem,
                                               as_stream(s));
   g_launches++;

@@ -51,23 +51,15 @@ __global__ void voxelize_params_kernel(const unsigned int *__restrict__ bounds, 
 
 struct VoxSlot {
   long long key;
-  int count;
-  int rank;
+  int id;   // dense voxel id in claim order (-1 until the claimer has initialised the voxel's rows)
+  int pad;
 };
 
-__global__ void __launch_bounds__(256) vox_clear_kernel(int4 *__restrict__ table, long long H, double *sums,
-                                                        int *maxidx, int *__restrict__ counters) {
+__global__ void __launch_bounds__(256) vox_clear_kernel(int4 *__restrict__ table, long long H,
+                                                        int *__restrict__ counters) {
   long long stride = (long long)gridDim.x * blockDim.x;
-  const int4 e = make_int4(-1, -1, 0, -1);
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < H; i += stride) {
-    table[i] = e;
-    if (sums) {
-      double2 z = make_double2(0.0, 0.0);
-      reinterpret_cast<double2 *>(sums)[i * 2] = z;
-      reinterpret_cast<double2 *>(sums)[i * 2 + 1] = z;
-    }
-    if (maxidx) maxidx[i] = -1;
-  }
+  const int4 e = make_int4(-1, -1, -1, 0);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < H; i += stride) table[i] = e;
   if (blockIdx.x == 0 && threadIdx.x < 4) counters[threadIdx.x] = 0;
 }
 
@@ -80,14 +72,17 @@ __device__ __forceinline__ long long vox_key(float4 p, const float *start, const
   return c0 * stride[0] + c1 * stride[1] + c2 * stride[2] + c3 * stride[3];
 }
 
-// insert + accumulate.  Lanes with equal keys are aggregated: one probe sequence per distinct voxel and
-// warp, counts added once; sums / max index still go through per-lane atomics (fp64 add, int max).
+// insert + accumulate.  The hash table only maps a cell key to a DENSE voxel id (claim order); everything per voxel
+// (count, fp64 sums, max index) lives in arrays indexed by that id, so the random traffic of this pass and of the
+// finishing passes goes to V-row arrays (L2-sized for the sequences of this path) instead of the H-slot table.
+// Lanes with equal keys are aggregated: one probe sequence per distinct voxel and warp, counts added once; sums /
+// max index still go through per-lane atomics (fp64 add, int max).
 __global__ void __launch_bounds__(256)
 vox_insert_kernel(const float4 *__restrict__ pts, long long n, const float *__restrict__ start_d,
                   const long long *__restrict__ stride_d, float s0, float s1, float s2, float s3, int ignore_dim0,
-                  VoxSlot *__restrict__ table, long long mask, int *__restrict__ pt_slot, double *__restrict__ sums,
-                  int *__restrict__ maxidx, long long *__restrict__ ukeys, int *__restrict__ uslots,
-                  int *__restrict__ counters) {
+                  VoxSlot *__restrict__ table, long long mask, int *__restrict__ pt_vid, double *__restrict__ sums,
+                  int *__restrict__ maxidx, int *__restrict__ counts, long long *__restrict__ ukeys,
+                  int *__restrict__ uids, int *__restrict__ counters) {
   __shared__ float start[4];
   __shared__ long long stride[4];
   if (threadIdx.x < 4) {
@@ -109,37 +104,57 @@ vox_insert_kernel(const float4 *__restrict__ pts, long long n, const float *__re
     }
     unsigned int peers = __match_any_sync(0xffffffffu, key);
     int leader = __ffs(peers) - 1;
-    long long slot = -1;
+    int vid = -1;
     if (valid && lane == leader) {
-      slot = hash_key(key) & mask;
-      for (long long probes = 0;; ++probes) {
-        if (probes > mask) {
-          atomicExch(&counters[2], PCS_ERR_TABLE_FULL);
-          slot = -1;
+      long long slot = hash_key(key) & mask;
+      bool found = false;
+      for (long long probes = 0; probes <= mask; ++probes) {
+        long long cur = *((volatile long long *)&table[slot].key);
+        if (cur == key) {
+          found = true;
           break;
         }
-        long long cur = *((volatile long long *)&table[slot].key);
-        if (cur == key) break;
         if (cur == PCS_EMPTY_KEY) {
           unsigned long long prev = atomicCAS((unsigned long long *)&table[slot].key,
                                               (unsigned long long)PCS_EMPTY_KEY, (unsigned long long)key);
           if (prev == (unsigned long long)PCS_EMPTY_KEY) {
-            int id = atomicAdd(&counters[0], 1);  // claimer appends the unique key
-            ukeys[id] = key;
-            uslots[id] = (int)slot;
+            // claimer: take the next dense id, initialise the voxel's rows, then publish the id
+            vid = atomicAdd(&counters[0], 1);
+            counts[vid] = 0;
+            if (sums) {
+              const double2 z = make_double2(0.0, 0.0);
+              reinterpret_cast<double2 *>(sums)[(long long)vid * 2] = z;
+              reinterpret_cast<double2 *>(sums)[(long long)vid * 2 + 1] = z;
+            }
+            if (maxidx) maxidx[vid] = -1;
+            ukeys[vid] = key;
+            uids[vid] = vid;
+            __threadfence();
+            *((volatile int *)&table[slot].id) = vid;
             break;
           }
-          if ((long long)prev == key) break;
+          if ((long long)prev == key) {
+            found = true;
+            break;
+          }
         }
         slot = (slot + 1) & mask;
       }
-      if (slot >= 0) atomicAdd(&table[slot].count, __popc(peers));
+      if (found) {
+        while ((vid = *((volatile int *)&table[slot].id)) < 0) {
+        }
+        __threadfence();
+      }
+      if (vid < 0)
+        atomicExch(&counters[2], PCS_ERR_TABLE_FULL);
+      else
+        atomicAdd(&counts[vid], __popc(peers));
     }
-    slot = __shfl_sync(0xffffffffu, slot, leader);
-    if (valid && slot >= 0) {
-      pt_slot[i] = (int)slot;
+    vid = __shfl_sync(0xffffffffu, vid, leader);
+    if (valid && vid >= 0) {
+      pt_vid[i] = vid;
       if (sums) {
-        double *s = sums + slot * 4;
+        double *s = sums + (long long)vid * 4;
         atomicAdd(s + 0, (double)p.x);
         atomicAdd(s + 1, (double)p.y);
         atomicAdd(s + 2, (double)p.z);
@@ -148,34 +163,38 @@ vox_insert_kernel(const float4 *__restrict__ pts, long long n, const float *__re
       if (maxidx) {
         // the highest index of the group: only the last peer lane needs to go to memory
         int top = 31 - __clz(peers);
-        if (lane == top) atomicMax(maxidx + slot, (int)i);
+        if (lane == top) atomicMax(maxidx + vid, (int)i);
       }
     }
   }
 }
 
-__global__ void __launch_bounds__(256) vox_rank_kernel(VoxSlot *__restrict__ table, const int *__restrict__ uslots_sorted,
-                                                       long long V, const double *__restrict__ sums,
-                                                       const int *__restrict__ maxidx, float4 *__restrict__ sampled,
-                                                       long long *__restrict__ maxidx_out, int *__restrict__ counts_out) {
+// r-th smallest key <-> dense id: rank_of[id] = r plus the per-voxel outputs in ascending-key order
+__global__ void __launch_bounds__(256) vox_rank_kernel(const int *__restrict__ ids_sorted, long long V,
+                                                       const double *__restrict__ sums,
+                                                       const int *__restrict__ maxidx, const int *__restrict__ counts,
+                                                       int *__restrict__ rank_of, float4 *__restrict__ sampled,
+                                                       long long *__restrict__ maxidx_out,
+                                                       int *__restrict__ counts_out) {
   long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= V) return;
-  int slot = uslots_sorted[r];
-  table[slot].rank = (int)r;
-  int c = table[slot].count;
+  const int id = ids_sorted[r];
+  rank_of[id] = (int)r;
+  const int c = counts[id];
   if (counts_out) counts_out[r] = c;
   if (sampled && sums) {
-    const double *s = sums + (long long)slot * 4;
+    const double2 a = reinterpret_cast<const double2 *>(sums)[(long long)id * 2];
+    const double2 b = reinterpret_cast<const double2 *>(sums)[(long long)id * 2 + 1];
     double inv = 1.0 / (double)(c > 0 ? c : 1);
-    sampled[r] = make_float4((float)(s[0] * inv), (float)(s[1] * inv), (float)(s[2] * inv), (float)(s[3] * inv));
+    sampled[r] = make_float4((float)(a.x * inv), (float)(a.y * inv), (float)(b.x * inv), (float)(b.y * inv));
   }
-  if (maxidx_out && maxidx) maxidx_out[r] = maxidx[slot];
+  if (maxidx_out && maxidx) maxidx_out[r] = maxidx[id];
 }
 
-__global__ void __launch_bounds__(256) vox_inv_kernel(const VoxSlot *__restrict__ table, const int *__restrict__ pt_slot,
+__global__ void __launch_bounds__(256) vox_inv_kernel(const int *__restrict__ rank_of, const int *__restrict__ pt_vid,
                                                       long long n, long long *__restrict__ inv) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) inv[i] = table[pt_slot[i]].rank;
+  if (i < n) inv[i] = rank_of[pt_vid[i]];
 }
 
 // ---- per-group upper median (robust_median) --------------------------------------------------------
@@ -237,17 +256,17 @@ int pcs_voxelize_params(pcs_stream_t s, const uint32_t *bounds, const float *siz
 }
 
 int pcs_voxelize_insert(pcs_stream_t s, const float *pts, int64_t n, const float *start, const int64_t *strides,
-                        const float *size, int ignore_dim0, void *table, int64_t H, int32_t *pt_slot, double *sums,
-                        int32_t *maxidx, int64_t *ukeys, int32_t *uslots, int32_t *counters) {
+                        const float *size, int ignore_dim0, void *table, int64_t H, int32_t *pt_vid, double *sums,
+                        int32_t *maxidx, int32_t *counts, int64_t *ukeys, int32_t *uids, int32_t *counters) {
   if (!table || H < 2 || (H & (H - 1)) || n < 0 || n >= (1LL << 31) || ((uintptr_t)pts & 15) || !counters ||
-      (n > 0 && (!pt_slot || !ukeys || !uslots)) || ((uintptr_t)sums & 15))
+      (n > 0 && (!pt_vid || !counts || !ukeys || !uids)) || ((uintptr_t)sums & 15))
     return set_error(PCS_ERR_BAD_ARG, "pcs_voxelize_insert: bad args");
   cudaStream_t st = as_stream(s);
-  PCS_LAUNCH(vox_clear_kernel, grid_for(H, 256, 8), 256, 0, st, (int4 *)table, (long long)H, sums, maxidx, counters);
+  PCS_LAUNCH(vox_clear_kernel, grid_for(H, 256, 8), 256, 0, st, (int4 *)table, (long long)H, counters);
   if (n == 0) return 0;
   PCS_LAUNCH(vox_insert_kernel, grid_for(n, 256, 8), 256, 0, st, (const float4 *)pts, (long long)n, start,
              (const long long *)strides, size[0], size[1], size[2], size[3], ignore_dim0, (VoxSlot *)table,
-             (long long)(H - 1), pt_slot, sums, maxidx, (long long *)ukeys, uslots, counters);
+             (long long)(H - 1), pt_vid, sums, maxidx, counts, (long long *)ukeys, uids, counters);
   return 0;
 }
 
@@ -272,18 +291,19 @@ int pcs_sort_pairs(pcs_stream_t s, const int64_t *keys_in, int64_t *keys_out, co
   return 0;
 }
 
-int pcs_voxelize_finish(pcs_stream_t s, void *table, int64_t H, const int32_t *uslots_sorted, int64_t V,
-                        const int32_t *pt_slot, int64_t n, const double *sums, const int32_t *maxidx, int64_t *inv,
-                        float *sampled, int64_t *maxidx_out, int32_t *counts_out) {
-  if (!table || V < 0 || n < 0 || ((uintptr_t)sampled & 15))
+int pcs_voxelize_finish(pcs_stream_t s, const int32_t *ids_sorted, int64_t V, const int32_t *pt_vid, int64_t n,
+                        const double *sums, const int32_t *maxidx, const int32_t *counts, int32_t *rank_of,
+                        int64_t *inv, float *sampled, int64_t *maxidx_out, int32_t *counts_out) {
+  if (V < 0 || n < 0 || ((uintptr_t)sampled & 15) || ((uintptr_t)sums & 15) ||
+      (V > 0 && (!ids_sorted || !counts || !rank_of)) || (n > 0 && inv && !pt_vid))
     return set_error(PCS_ERR_BAD_ARG, "pcs_voxelize_finish: bad args");
   cudaStream_t st = as_stream(s);
   if (V > 0)
-    PCS_LAUNCH(vox_rank_kernel, (unsigned)((V + 255) / 256), 256, 0, st, (VoxSlot *)table, uslots_sorted,
-               (long long)V, sums, maxidx, (float4 *)sampled, (long long *)maxidx_out, counts_out);
+    PCS_LAUNCH(vox_rank_kernel, (unsigned)((V + 255) / 256), 256, 0, st, ids_sorted, (long long)V, sums, maxidx,
+               counts, rank_of, (float4 *)sampled, (long long *)maxidx_out, counts_out);
   if (n > 0 && inv)
-    PCS_LAUNCH(vox_inv_kernel, (unsigned)((n + 255) / 256), 256, 0, st, (const VoxSlot *)table, pt_slot,
-               (long long)n, (long long *)inv);
+    PCS_LAUNCH(vox_inv_kernel, (unsigned)((n + 255) / 256), 256, 0, st, rank_of, pt_vid, (long long)n,
+               (long long *)inv);
   return 0;
 }
 

@@ -12,21 +12,27 @@ import torch
 _SKIP_KEYS = ("frame_id", "metadata", "calib", "obj_ids")
 
 
+def _host_tensor(key, val):
+    """CPU tensor to be moved for this key, or None when the value stays as it is (reference key rules)."""
+    if key in _SKIP_KEYS:
+        return None
+    if isinstance(val, np.ndarray):
+        if val.dtype.kind not in "fiub":
+            return None
+        val = torch.from_numpy(val)
+    if isinstance(val, torch.Tensor) and val.device.type == "cpu":
+        return val.int() if key == "image_shape" else val
+    return None
+
+
 def load_data_to_gpu(batch_dict, device=None, non_blocking=True):
     """In-place move of the array / CPU-tensor values of a collated batch to `device` (same key rules as the
     reference; numpy arrays and CPU tensors are both accepted, pinned tensors are copied asynchronously)."""
     device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
     for key, val in batch_dict.items():
-        if key in _SKIP_KEYS:
-            continue
-        if isinstance(val, np.ndarray):
-            if val.dtype.kind not in "fiub":
-                continue
-            val = torch.from_numpy(val)
-        if isinstance(val, torch.Tensor) and val.device.type == "cpu":
-            if key == "image_shape":
-                val = val.int()
-            batch_dict[key] = val.to(device, non_blocking=non_blocking)
+        src = _host_tensor(key, val)
+        if src is not None:
+            batch_dict[key] = src.to(device, non_blocking=non_blocking)
     return batch_dict
 
 
@@ -35,6 +41,11 @@ class DevicePrefetcher:
 
         for batch in DevicePrefetcher(loader, device):
             model(batch)
+
+    The destination tensors are allocated from the compute stream's pool (so the blocks of the batch consumed two
+    steps ago are reused and the steady state performs no cudaMalloc); the copies run on a side stream that first
+    waits for the work already enqueued on the compute stream, i.e. the copy of batch k+1 overlaps the processing
+    of batch k.
     """
 
     def __init__(self, batches, device):
@@ -50,10 +61,25 @@ class DevicePrefetcher:
         except StopIteration:
             self.next_batch = None
             return
-        with torch.cuda.stream(self.stream):
-            self.next_batch = load_data_to_gpu(dict(host), self.device, non_blocking=True)
-            self.ready = torch.cuda.Event()
-            self.ready.record(self.stream)
+        batch = dict(host)
+        cur = torch.cuda.current_stream(self.device)
+        pairs = []
+        with torch.cuda.device(self.device):
+            for key, val in batch.items():
+                src = _host_tensor(key, val)
+                if src is not None:
+                    dst = torch.empty(src.shape, dtype=src.dtype, device=self.device)
+                    batch[key] = dst
+                    pairs.append((dst, src))
+            free_at = torch.cuda.Event()
+            free_at.record(cur)  # recycled blocks may still be read by kernels enqueued so far
+            self.stream.wait_event(free_at)
+            with torch.cuda.stream(self.stream):
+                for dst, src in pairs:
+                    dst.copy_(src, non_blocking=True)
+                self.ready = torch.cuda.Event()
+                self.ready.record(self.stream)
+        self.next_batch = batch
 
     def __iter__(self):
         return self
@@ -61,11 +87,7 @@ class DevicePrefetcher:
     def __next__(self):
         if self.next_batch is None:
             raise StopIteration
-        cur = torch.cuda.current_stream(self.device)
-        cur.wait_event(self.ready)
+        torch.cuda.current_stream(self.device).wait_event(self.ready)
         batch = self.next_batch
-        for v in batch.values():
-            if isinstance(v, torch.Tensor) and v.is_cuda:
-                v.record_stream(cur)  # allocated on the staging stream, consumed on the compute stream
         self._stage()
         return batch

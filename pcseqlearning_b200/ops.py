@@ -363,17 +363,19 @@ def voxelize(points, grid_size, ignore_dim0=False, want_mean=True, want_max=Fals
         strides = torch.empty(5, dtype=torch.int64, device=dev)
         _lib.check(L.pcs_voxelize_params(s, _ptr(bounds), _f4(size), int(ignore_dim0), _ptr(start), _ptr(strides)),
                    "pcs_voxelize_params")
-        H = next_pow2(max(2 * n, 1024))
+        H = next_pow2(max(n + n // 4, 1024))  # load factor <= 0.8 even if every point had its own voxel
         table = torch.empty(H, 4, dtype=torch.int32, device=dev)
-        pt_slot = torch.empty(n, dtype=torch.int32, device=dev)
-        sums = torch.empty(H, 4, dtype=torch.float64, device=dev) if want_mean else None
-        maxidx = torch.empty(H, dtype=torch.int32, device=dev) if want_max else None
+        pt_vid = torch.empty(n, dtype=torch.int32, device=dev)
+        # per-voxel rows are indexed by dense id: n rows allocated, the first V touched
+        sums = torch.empty(n, 4, dtype=torch.float64, device=dev) if want_mean else None
+        maxidx = torch.empty(n, dtype=torch.int32, device=dev) if want_max else None
+        cnt = torch.empty(n, dtype=torch.int32, device=dev)
         ukeys = torch.empty(n, dtype=torch.int64, device=dev)
-        uslots = torch.empty(n, dtype=torch.int32, device=dev)
+        uids = torch.empty(n, dtype=torch.int32, device=dev)
         counters = torch.empty(4, dtype=torch.int32, device=dev)
         _lib.check(L.pcs_voxelize_insert(s, _ptr(pts), n, _ptr(start), _ptr(strides), _f4(size), int(ignore_dim0),
-                                         _ptr(table), H, _ptr(pt_slot), _ptr(sums), _ptr(maxidx), _ptr(ukeys),
-                                         _ptr(uslots), _ptr(counters)), "pcs_voxelize_insert")
+                                         _ptr(table), H, _ptr(pt_vid), _ptr(sums), _ptr(maxidx), _ptr(cnt),
+                                         _ptr(ukeys), _ptr(uids), _ptr(counters)), "pcs_voxelize_insert")
         c = counters.tolist()  # host sync: V is needed to size the outputs
         if c[2] != 0:
             raise _lib.PcsError(f"voxelize failed on device (code {c[2]})")
@@ -381,15 +383,16 @@ def voxelize(points, grid_size, ignore_dim0=False, want_mean=True, want_max=Fals
         tb = int(L.pcs_sort_pairs_tmp_bytes(V))
         tmp = torch.empty(tb, dtype=torch.uint8, device=dev)
         keys_sorted = torch.empty(V, dtype=torch.int64, device=dev)
-        slots_sorted = torch.empty(V, dtype=torch.int32, device=dev)
-        _lib.check(L.pcs_sort_pairs(s, _ptr(ukeys), _ptr(keys_sorted), _ptr(uslots), _ptr(slots_sorted), V, _ptr(tmp),
+        ids_sorted = torch.empty(V, dtype=torch.int32, device=dev)
+        _lib.check(L.pcs_sort_pairs(s, _ptr(ukeys), _ptr(keys_sorted), _ptr(uids), _ptr(ids_sorted), V, _ptr(tmp),
                                     tb), "pcs_sort_pairs")
         inv = torch.empty(n, dtype=torch.int64, device=dev)
+        rank_of = torch.empty(max(V, 1), dtype=torch.int32, device=dev)
         sampled = torch.empty(V, 4, dtype=torch.float32, device=dev) if want_mean else None
         maxidx_out = torch.empty(V, dtype=torch.int64, device=dev) if want_max else None
         counts = torch.empty(V, dtype=torch.int32, device=dev) if want_counts else None
-        _lib.check(L.pcs_voxelize_finish(s, _ptr(table), H, _ptr(slots_sorted), V, _ptr(pt_slot), n, _ptr(sums),
-                                         _ptr(maxidx), _ptr(inv), _ptr(sampled), _ptr(maxidx_out), _ptr(counts)),
+        _lib.check(L.pcs_voxelize_finish(s, _ptr(ids_sorted), V, _ptr(pt_vid), n, _ptr(sums), _ptr(maxidx), _ptr(cnt),
+                                         _ptr(rank_of), _ptr(inv), _ptr(sampled), _ptr(maxidx_out), _ptr(counts)),
                    "pcs_voxelize_finish")
     out.update(inv=inv, num=V, keys=keys_sorted)
     if want_mean:
