@@ -237,6 +237,12 @@ int pcs_smooth_velo(pcs_stream_t s, float *velos, const float *diffs, float *m, 
  * broadcast of the ground stage (preprocessor_utils.py:416-419). */
 int pcs_gather_rows(pcs_stream_t s, const void *src, const int64_t *idx, int64_t n, int row_bytes, void *dst);
 
+/* Per-group min and max of a float column: out_min / out_max float[C] (empty groups -> 0, the torch_scatter
+ * convention), values[i * stride], ids int64[n] in [0, C) (rows sorted by group reduce per warp before the atomics),
+ * tmp uint32[2 * C] scratch.  Replaces the scatter(min) / scatter(max) pair of preprocessor_utils.py:113-114. */
+int pcs_group_minmax(pcs_stream_t s, const float *values, int64_t stride, const int64_t *ids, int64_t n, int64_t C,
+                     uint32_t *tmp, float *out_min, float *out_max);
+
 #ifdef __cplusplus
 }
 #endif

@@ -61,6 +61,8 @@ _SIGNATURES = {
                                 c_void_p]),
     "pcs_smooth_velo": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float,
                                 c_float, c_int, c_float, c_void_p]),
+    "pcs_group_minmax": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_void_p,
+                                 c_void_p]),
     "pcs_gather_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "pcs_group_median": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p,
                                  c_void_p]),

@@ -325,3 +325,79 @@ extern "C" int pcs_gather_rows(pcs_stream_t s, const void *src, const int64_t *i
   }
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Per-group min / max of a float column (torch_scatter.scatter(min|max) of preprocessor_utils.py:113-114 and the
+// pillar statistics of format_pillars): order-preserving uint encoding + atomicMin / atomicMax.  A warp whose 32
+// rows belong to one group (the common case: rows sorted by group) reduces with redux first and issues ONE pair of
+// atomics; torch's scatter_reduce issues one contended atomic per row.
+// ------------------------------------------------------------------------------------------------
+namespace pcs {
+
+__global__ void __launch_bounds__(256) minmax_init_kernel(unsigned int *__restrict__ mn, unsigned int *__restrict__ mx,
+                                                          long long C) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < C) {
+    mn[i] = 0xffffffffu;
+    mx[i] = 0u;
+  }
+}
+
+__global__ void __launch_bounds__(256) minmax_scatter_kernel(const float *__restrict__ val, long long stride,
+                                                             const long long *__restrict__ ids, long long n,
+                                                             long long C, unsigned int *__restrict__ mn,
+                                                             unsigned int *__restrict__ mx) {
+  const int lane = threadIdx.x & 31;
+  const long long nround = (n + 31) / 32 * 32;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nround;
+       i += (long long)gridDim.x * blockDim.x) {
+    const bool valid = i < n;
+    long long g = -1;
+    unsigned int o = 0u;
+    if (valid) {
+      g = ids[i];
+      o = f2ord(val[i * stride]);
+      if (g < 0 || g >= C) g = -1;  // out-of-range ids are ignored
+    }
+    const long long g0 = __shfl_sync(0xffffffffu, g, 0);
+    if (__all_sync(0xffffffffu, g == g0 || !valid)) {
+      const unsigned int lo = __reduce_min_sync(0xffffffffu, valid ? o : 0xffffffffu);
+      const unsigned int hi = __reduce_max_sync(0xffffffffu, valid ? o : 0u);
+      if (lane == 0 && g0 >= 0) {
+        atomicMin(mn + g0, lo);
+        atomicMax(mx + g0, hi);
+      }
+    } else if (g >= 0) {
+      atomicMin(mn + g, o);
+      atomicMax(mx + g, o);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) minmax_finish_kernel(const unsigned int *__restrict__ mn,
+                                                            const unsigned int *__restrict__ mx, long long C,
+                                                            float *__restrict__ out_min, float *__restrict__ out_max) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < C) {
+    const bool empty = mn[i] == 0xffffffffu && mx[i] == 0u;  // empty groups -> 0 (torch_scatter convention)
+    out_min[i] = empty ? 0.f : ord2f(mn[i]);
+    out_max[i] = empty ? 0.f : ord2f(mx[i]);
+  }
+}
+
+}  // namespace pcs
+
+extern "C" int pcs_group_minmax(pcs_stream_t s, const float *values, int64_t stride, const int64_t *ids, int64_t n,
+                                int64_t C, uint32_t *tmp, float *out_min, float *out_max) {
+  using namespace pcs;
+  if (n < 0 || C < 1 || stride < 1 || !tmp || !out_min || !out_max || (n > 0 && (!values || !ids)))
+    return set_error(PCS_ERR_BAD_ARG, "pcs_group_minmax: bad args");
+  cudaStream_t st = as_stream(s);
+  PCS_LAUNCH(minmax_init_kernel, (unsigned)((C + 255) / 256), 256, 0, st, tmp, tmp + C, (long long)C);
+  if (n > 0)
+    PCS_LAUNCH(minmax_scatter_kernel, grid_for(n, 256, 8), 256, 0, st, values, (long long)stride,
+               (const long long *)ids, (long long)n, (long long)C, tmp, tmp + C);
+  PCS_LAUNCH(minmax_finish_kernel, (unsigned)((C + 255) / 256), 256, 0, st, tmp, tmp + C, (long long)C, out_min,
+             out_max);
+  return 0;
+}

@@ -622,6 +622,22 @@ def cluster_labels_multi(fxyz, radii, max_num_neighbors=32, chunk=10, num_frames
     return labels, n_comp
 
 
+def group_minmax(values, ids, num_groups):
+    """(min, max) of float `values` [n] per group `ids` int64[n] -> two f32[num_groups] (empty groups 0): the
+    scatter(min) / scatter(max) pair of the ground stage in one pass.  `values` may be a strided column view."""
+    assert values.dim() == 1 and values.dtype == torch.float32 and values.is_cuda
+    ids = ids.long().contiguous()
+    n, dev, C = values.shape[0], values.device, int(num_groups)
+    stride = values.stride(0) if n > 1 else 1
+    tmp = torch.empty(2 * C, dtype=torch.int32, device=dev)
+    out_min = torch.empty(C, dtype=torch.float32, device=dev)
+    out_max = torch.empty(C, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().pcs_group_minmax(_stream(), _ptr(values), stride, _ptr(ids), n, C, _ptr(tmp),
+                                               _ptr(out_min), _ptr(out_max)), "pcs_group_minmax")
+    return out_min, out_max
+
+
 def gather_rows(src, idx):
     """src[idx] for a contiguous tensor whose rows are 1, 4, 8, 12 or 16 bytes (anything else falls back to torch
     indexing).  idx: int64 row indices."""

@@ -93,8 +93,11 @@ def compute_min_height_from_ransac(pillar_dims, num_pillars, voxels, pillars, cf
     cxyz = voxels.bxyz[order, 1:]
     cidx = cidx[order]
     z = cxyz[:, -1]
-    c_min_z = scatter_min(z, cidx, num_coarse)
-    c_max_z = scatter_max(z, cidx, num_coarse)
+    if use_kernels:
+        c_min_z, c_max_z = ops.group_minmax(z, cidx, num_coarse)  # one pass, warp-reduced (rows are sorted by cidx)
+    else:
+        c_min_z = scatter_min(z, cidx, num_coarse)
+        c_max_z = scatter_max(z, cidx, num_coarse)
     best_conf = torch.zeros_like(c_min_z)
     best_normal = c_min_z.new_zeros(num_coarse, 3)
     best_normal[:, -1] = 1.0

@@ -76,3 +76,20 @@ def test_ransac_kernel_vs_torch_irls(golden_dir):
         outs.append(pillars.min_z)
     d = (outs[0] - outs[1]).abs()
     assert float(d.median()) < 1e-3 and float((d < 2e-2).float().mean()) > 0.98, (float(d.median()), float(d.max()))
+
+
+@pytest.mark.gpu
+def test_group_minmax_matches_torch_scatter():
+    """pcs_group_minmax vs torch scatter_reduce(amin / amax) (the torch_scatter semantics of the reference,
+    preprocessor_utils.py:113-114): sorted and unsorted ids, strided column, empty groups -> 0."""
+    from pcseqlearning_b200 import ops
+    from pcseqlearning_b200.utils.scatter import scatter_max, scatter_min
+    g = torch.Generator(device="cpu").manual_seed(3)
+    for n, C, sort in [(100000, 700, True), (5000, 64, False), (33, 5, True), (1, 3, True)]:
+        xyz = torch.randn(n, 3, generator=g).cuda() * 7
+        ids = torch.randint(0, max(C - 2, 1), (n,), generator=g).cuda()  # the last groups stay empty
+        if sort:
+            ids = ids.sort().values
+        z = xyz[:, -1]
+        mn, mx = ops.group_minmax(z, ids, C)
+        assert torch.equal(mn, scatter_min(z, ids, C)) and torch.equal(mx, scatter_max(z, ids, C))
