@@ -183,6 +183,12 @@ def run_ours(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        # connect the communicator now: NCCL's lazy set-up (proxy threads, channel buffers) otherwise lands on the
+        # first timed steps of every rank
+        t = torch.zeros(1, device=dev)
+        dist.all_reduce(t)
+        dist.barrier()
+        torch.cuda.synchronize()
     t0 = time.time()
     # every rank processes the SAME synthetic sequence (identical work per GPU: replicas / weak scaling)
     cache = args.cache and f"{args.cache}.f{args.frames}.pt"
