@@ -47,6 +47,9 @@ __device__ __forceinline__ float ord2f(unsigned int o) {
   return __uint_as_float(b);
 }
 
+// L1 prefetch of the line holding *p (no register, no dependency: hides the latency of a load issued later)
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 // ---- streaming 128-bit loads ----------------------------------------------------------------------
 __device__ __forceinline__ float4 ldg_stream_f4(const float4 *p) {
   float4 v;

@@ -67,6 +67,7 @@ struct RansacArgs {
   float sigma2;
   float stopping_delta;
   int max_iter;
+  int prefetch;  // 1: prefetch the voxels of the warp's next step into L1 while the current step is evaluated
 };
 
 struct PlaneN {  // plane being evaluated: centre, normal
@@ -227,6 +228,10 @@ __device__ void ransac_step(const RansacArgs &A, long long v0, long long v1, int
         if (valid) {
           pid = __ldg(A.cidx + i);
           p = __ldg(A.vox + i);
+        }
+        if (A.prefetch && i + nwarp * 32 < b) {
+          prefetch_l1(A.vox + i + nwarp * 32);
+          if ((lane & 7) == 0) prefetch_l1(A.cidx + i + nwarp * 32);
         }
         const int pl0 = __shfl_sync(0xffffffffu, pid, 0);
         const bool uniform = __all_sync(0xffffffffu, (!valid) || pid == pl0) && pl0 >= 0;
@@ -770,6 +775,10 @@ int pcs_ground_ransac(pcs_stream_t s, const float *vox, const int32_t *cidx, con
   A.sigma2 = sigma2;
   A.stopping_delta = stopping_delta;
   A.max_iter = max_iter;
+  {
+    const char *e = getenv("PCS_RANSAC_PREFETCH");
+    A.prefetch = e ? atoi(e) : 0;
+  }
   int dev = 0, sms = 148, per_sm = 1;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -26,6 +26,7 @@ struct QueryRange {
   int range[4];
   int nc;
   int append;  // 1: append-then-sort list building, 0: sorted insertion from the first candidate
+  int prefetch;  // 1: every lane prefetches the first rows of the cell it found (the sweeps come later, one by one)
 };
 
 // Up to three union-find forests fed by one search (multi-radius cluster proposals): forest k receives the list
@@ -159,7 +160,13 @@ radius_search_kernel(const pcs_slot_t *__restrict__ table, long long mask, const
               slot = (slot + 1) & (unsigned int)mask;
             }
           }
-          if (count > 0) sel = (__float_as_uint(dmin2) & ~31u) | (unsigned int)lane;
+          if (count > 0) {
+            sel = (__float_as_uint(dmin2) & ~31u) | (unsigned int)lane;
+            if (qr.prefetch) {  // the up-to-27 cell rows are fetched concurrently instead of one miss per visit
+              prefetch_l1(sorted_pts + start);
+              prefetch_l1(sorted_idx + start);
+            }
+          }
         }
       }
 
@@ -312,6 +319,8 @@ int pcs_radius_search(pcs_stream_t s, const pcs_slot_t *table, int64_t H, const 
   {
     const char *e = getenv("PCS_SEARCH_APPEND");
     qr.append = e ? atoi(e) : 1;
+    const char *p = getenv("PCS_SEARCH_PREFETCH");
+    qr.prefetch = p ? atoi(p) : 1;
   }
   for (int i = 0; i < 4; i++) {
     qr.qmin[i] = qmin[i];

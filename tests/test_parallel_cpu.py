@@ -91,3 +91,21 @@ def test_globalize_component_ids_two_ranks(golden_dir, tmp_path):
         p.join(180)
         assert p.exitcode == 0
     assert np.load(os.path.join(tmp_path, "result.npy")).tolist() == [1, 1, 1]
+
+
+def test_data_staging_key_rules_cpu():
+    """Host-side key rules of load_data_to_gpu / DevicePrefetcher (reference: pcdet/models/__init__.py:44-56):
+    string / object arrays and the listed bookkeeping keys stay on the host, numeric arrays and CPU tensors move."""
+    import numpy as np
+    import torch
+    from pcseqlearning_b200.data_staging import _host_tensor
+    assert _host_tensor("frame_id", np.array(["a"])) is None
+    assert _host_tensor("obj_ids", np.arange(3)) is None
+    assert _host_tensor("metadata", np.zeros(2)) is None
+    assert _host_tensor("names", np.array(["x", "y"])) is None  # non-numeric arrays are left alone
+    assert _host_tensor("batch_size", 4) is None
+    t = _host_tensor("point_bxyz", np.zeros((5, 4), np.float32))
+    assert isinstance(t, torch.Tensor) and t.dtype == torch.float32 and t.shape == (5, 4)
+    assert _host_tensor("image_shape", np.array([[3, 4]], np.int64)).dtype == torch.int32
+    src = torch.zeros(3)
+    assert _host_tensor("point_feat", src) is src
