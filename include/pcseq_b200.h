@@ -81,6 +81,17 @@ int pcs_hash_build(pcs_stream_t s, const float *pts, int64_t n, int seg_div, int
                    const int64_t *seg_dims, const float *vs, pcs_slot_t *table, int64_t H, float *sorted_pts,
                    int32_t *sorted_idx, int32_t *counters, uint32_t *occ, int64_t occ_bits);
 
+/* Same result contract as pcs_hash_build, but the row ranges of the occupied cells are assigned in ascending KEY
+ * order (frame-major, z fastest) instead of table-slot (= hash) order: the cells of a frame are contiguous in
+ * sorted_pts and self-queries walk the grid coherently.  Costs a radix sort of the <= min(n, H) occupied cells
+ * (no host sync: unused entries are padded with INT64_MAX).  ws: 16-byte aligned scratch of
+ * pcs_hash_build_sorted_ws_bytes(n, H) bytes.  Staged for the next round: the default path does not use it yet. */
+int64_t pcs_hash_build_sorted_ws_bytes(int64_t n, int64_t H);
+int pcs_hash_build_sorted(pcs_stream_t s, const float *pts, int64_t n, int seg_div, int n_seg, const float *seg_lo,
+                          const int64_t *seg_dims, const float *vs, pcs_slot_t *table, int64_t H, float *sorted_pts,
+                          int32_t *sorted_idx, int32_t *counters, uint32_t *occ, int64_t occ_bits, void *ws,
+                          int64_t ws_bytes);
+
 /* ---- neighbour search -----------------------------------------------------------------------
  * Replaces radius_graph_gpu = count_radius_graph_degree_kernel + radius_graph_kernel
  * (torch_hash_kernel.cu:224-409, 487-561) in ONE pass: for every query the cells

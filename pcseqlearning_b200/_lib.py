@@ -27,6 +27,10 @@ _SIGNATURES = {
                                c_void_p]),
     "pcs_hash_build": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64]),
+    "pcs_hash_build_sorted_ws_bytes": (c_int64, [c_int64, c_int64]),
+    "pcs_hash_build_sorted": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
+                                      c_int64]),
     "pcs_radius_search": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
                                   c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,

@@ -3,6 +3,8 @@
 // Replaces, for the cluster-tracking path, the torch ops of RadiusGraph.build_graph
 // (pcdet/models/model_utils/graph_utils.py:169-183) and hash_insert_gpu
 // (pcdet/ops/torch_hash/src/torch_hash_kernel.cu:54-91).  See include/pcseq_b200.h.
+#include <cub/device/device_radix_sort.cuh>
+
 #include "common.cuh"
 
 namespace pcs {
@@ -291,6 +293,45 @@ __global__ void __launch_bounds__(256) rewind_ranges_kernel(pcs_slot_t *__restri
   }
 }
 
+// ---- key-ordered cell ranges (pcs_hash_build_sorted) ---------------------------------------------
+// assign_ranges_kernel hands out row ranges in SLOT order, i.e. in hash order: the 27 neighbour cells of a query end
+// up scattered over sorted_pts.  The variant below numbers the occupied cells by ascending key instead (frame-major,
+// z fastest), so a frame's cells are contiguous and self-queries walk the grid coherently.
+__global__ void __launch_bounds__(256) fill_keys_kernel(long long *__restrict__ keys, long long cap) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < cap) keys[i] = 0x7fffffffffffffffLL;
+}
+
+__global__ void __launch_bounds__(256) collect_cells_kernel(const pcs_slot_t *__restrict__ table, long long H,
+                                                            long long *__restrict__ keys, int *__restrict__ slots,
+                                                            long long cap, int *__restrict__ cursor) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= H) return;
+  const long long k = table[i].key;
+  if (k == PCS_EMPTY_KEY) return;
+  const int r = atomicAdd(cursor, 1);
+  if (r < cap) {
+    keys[r] = k;
+    slots[r] = (int)i;
+  }
+}
+
+__global__ void __launch_bounds__(256) gather_counts_kernel(const pcs_slot_t *__restrict__ table,
+                                                            const long long *__restrict__ keys_sorted,
+                                                            const int *__restrict__ slots_sorted, long long cap,
+                                                            int *__restrict__ cnt) {
+  long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < cap) cnt[r] = keys_sorted[r] == 0x7fffffffffffffffLL ? 0 : table[slots_sorted[r]].count;
+}
+
+__global__ void __launch_bounds__(256) scatter_starts_kernel(pcs_slot_t *__restrict__ table,
+                                                             const long long *__restrict__ keys_sorted,
+                                                             const int *__restrict__ slots_sorted,
+                                                             const long long *__restrict__ offs, long long cap) {
+  long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < cap && keys_sorted[r] != 0x7fffffffffffffffLL) table[slots_sorted[r]].start = (int)offs[r];
+}
+
 }  // namespace pcs
 
 using namespace pcs;
@@ -364,5 +405,82 @@ int pcs_hash_build(pcs_stream_t s, const float *pts, int64_t n, int seg_div, int
   PCS_LAUNCH(rewind_ranges_kernel, (unsigned)((H + 255) / 256), 256, 0, st, table, (long long)H);
   return 0;
 }
+
+/* ---- staged for the next round: cell ranges in key order (not used by the default path yet) ---- */
+static inline int64_t align256(int64_t b) { return (b + 255) / 256 * 256; }
+
+static int64_t sorted_ws_layout(int64_t cap, int64_t off[8]) {
+  size_t cub_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const unsigned long long *)nullptr,
+                                  (unsigned long long *)nullptr, (const int *)nullptr, (int *)nullptr, (int)cap);
+  int64_t o = 0;
+  off[0] = o; o += align256(cap * 8);                              // keys_in
+  off[1] = o; o += align256(cap * 8);                              // keys_out
+  off[2] = o; o += align256(cap * 4);                              // slots_in
+  off[3] = o; o += align256(cap * 4);                              // slots_out
+  off[4] = o; o += align256(cap * 4);                              // cnt
+  off[5] = o; o += align256((cap + 1) * 8);                        // offs
+  off[6] = o; o += align256(pcs_exclusive_scan_tmp_bytes(cap));    // scan scratch
+  off[7] = o; o += align256((int64_t)cub_bytes + 256);             // CUB scratch
+  return o + 256;
+}
+
+int64_t pcs_hash_build_sorted_ws_bytes(int64_t n, int64_t H) {
+  int64_t off[8];
+  const int64_t cap = n < H ? n : H;
+  return sorted_ws_layout(cap < 1 ? 1 : cap, off);
+}
+
+int pcs_hash_build_sorted(pcs_stream_t s, const float *pts, int64_t n, int seg_div, int n_seg, const float *seg_lo,
+                          const int64_t *seg_dims, const float *vs, pcs_slot_t *table, int64_t H, float *sorted_pts,
+                          int32_t *sorted_idx, int32_t *counters, uint32_t *occ, int64_t occ_bits, void *ws,
+                          int64_t ws_bytes) {
+  if (occ && (occ_bits < 32 || occ_bits > (1LL << 32) || (occ_bits & (occ_bits - 1))))
+    return set_error(PCS_ERR_BAD_ARG, "pcs_hash_build_sorted: occ_bits must be a power of two in [32, 2^32]");
+  int occ_shift = 0;
+  if (occ) {
+    int lg = 0;
+    while ((1LL << lg) < occ_bits) ++lg;
+    occ_shift = 32 - lg;
+  }
+  if (!table || !counters || H < 2 || (H & (H - 1)) || n_seg < 1 || n_seg > PCS_MAX_SEGMENTS || n < 0 ||
+      n >= (1LL << 31) || ((uintptr_t)pts & 15) || ((uintptr_t)sorted_pts & 15) || ((uintptr_t)table & 15) || !ws ||
+      ((uintptr_t)ws & 15) || ws_bytes < pcs_hash_build_sorted_ws_bytes(n, H))
+    return set_error(PCS_ERR_BAD_ARG, "pcs_hash_build_sorted: bad args / workspace too small");
+  cudaStream_t st = as_stream(s);
+  SegGeom g = make_geom(seg_lo, seg_dims, vs, seg_div, n_seg);
+  PCS_LAUNCH(table_clear_kernel, grid_for(H, 256, 8), 256, 0, st, (int4 *)table, (long long)H, counters, occ,
+             occ ? (long long)(occ_bits >> 5) : 0LL);
+  if (n == 0) return 0;
+  PCS_LAUNCH(hash_count_kernel, grid_for(n, 256, 8), 256, 0, st, (const float4 *)pts, (long long)n, g, table,
+             (long long)(H - 1), counters, occ, occ_shift);
+  const int64_t cap = n < H ? n : H;  // an upper bound of the number of occupied cells, known without a host sync
+  int64_t off[8];
+  sorted_ws_layout(cap, off);
+  char *w = (char *)ws;
+  long long *keys_in = (long long *)(w + off[0]), *keys_out = (long long *)(w + off[1]);
+  int *slots_in = (int *)(w + off[2]), *slots_out = (int *)(w + off[3]), *cnt = (int *)(w + off[4]);
+  long long *offs = (long long *)(w + off[5]);
+  const unsigned blocks_cap = (unsigned)((cap + 255) / 256);
+  PCS_LAUNCH(fill_keys_kernel, blocks_cap, 256, 0, st, keys_in, (long long)cap);
+  // counters[3] is the append cursor of the collection pass (cleared by table_clear_kernel)
+  PCS_LAUNCH(collect_cells_kernel, (unsigned)((H + 255) / 256), 256, 0, st, table, (long long)H, keys_in, slots_in,
+             (long long)cap, counters + 3);
+  size_t cub_bytes = (size_t)(ws_bytes - off[7]);
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(w + off[7], cub_bytes, (const unsigned long long *)keys_in,
+                                                  (unsigned long long *)keys_out, slots_in, slots_out, (int)cap, 0, 64,
+                                                  st);
+  g_launches += 8;
+  if (e != cudaSuccess) return set_error((int)e, "pcs_hash_build_sorted: cub::DeviceRadixSort::SortPairs");
+  PCS_LAUNCH(gather_counts_kernel, blocks_cap, 256, 0, st, table, keys_out, slots_out, (long long)cap, cnt);
+  int rc = pcs_exclusive_scan(s, cnt, cap, (int64_t *)offs, w + off[6], pcs_exclusive_scan_tmp_bytes(cap));
+  if (rc != 0) return rc;
+  PCS_LAUNCH(scatter_starts_kernel, blocks_cap, 256, 0, st, table, keys_out, slots_out, offs, (long long)cap);
+  PCS_LAUNCH(hash_scatter_kernel, grid_for(n, 256, 8), 256, 0, st, (const float4 *)pts, (long long)n, g, table,
+             (long long)(H - 1), (float4 *)sorted_pts, sorted_idx);
+  PCS_LAUNCH(rewind_ranges_kernel, (unsigned)((H + 255) / 256), 256, 0, st, table, (long long)H);
+  return 0;
+}
+
 
 }  // extern "C"

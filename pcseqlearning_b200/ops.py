@@ -13,6 +13,7 @@ from . import _lib
 
 PCS_MAX_K = 32
 PCS_MAX_SEGMENTS = 64
+GRID_SORTED = int(os.environ.get("PCS_GRID_SORTED", "0"))  # staged: key-ordered cell ranges in the proposal grids
 OCC_BITS_PER_SLOT = int(os.environ.get("PCS_OCC_BITS_PER_SLOT", "16"))  # 0 disables the occupancy bitmap
 
 # Optional per-kernel CUDA-event log (bench.py's roofline leg): name -> list of (start, end, meta)
@@ -96,7 +97,8 @@ class CellGrid:
     origin (the reference uses ref U query, graph_utils.py:171-173).
     """
 
-    def __init__(self, ref, voxel_size, bounds_sets=None, seg_div=1, n_seg=1, table_size=None, pad=0, geometry=None):
+    def __init__(self, ref, voxel_size, bounds_sets=None, seg_div=1, n_seg=1, table_size=None, pad=0, geometry=None,
+                 sorted_cells=False):
         L = _lib.lib()
         self.ref = _as_points(ref, "ref")
         dev = self.ref.device
@@ -133,10 +135,19 @@ class CellGrid:
             self.occ_bits = min(max(self.H * OCC_BITS_PER_SLOT, 32), 1 << 32) if OCC_BITS_PER_SLOT > 0 else 0
             self.occ = torch.empty(self.occ_bits // 32, dtype=torch.int32, device=dev) if self.occ_bits else None
             with _timed("hash_build", n=self.n, H=self.H):
-                _lib.check(L.pcs_hash_build(s, _ptr(self.ref), self.n, self.seg_div, self.n_seg, _ptr(self.seg_lo),
-                                            _ptr(self.seg_dims), _f4(self.vs), _ptr(self.table), self.H,
-                                            _ptr(self.sorted_pts), _ptr(self.sorted_idx), _ptr(self.counters),
-                                            _ptr(self.occ), self.occ_bits), "pcs_hash_build")
+                if sorted_cells:  # staged: cell ranges in key order (frame-major), see pcs_hash_build_sorted
+                    wb = int(L.pcs_hash_build_sorted_ws_bytes(self.n, self.H))
+                    ws = torch.empty(wb, dtype=torch.uint8, device=dev)
+                    _lib.check(L.pcs_hash_build_sorted(s, _ptr(self.ref), self.n, self.seg_div, self.n_seg,
+                                                       _ptr(self.seg_lo), _ptr(self.seg_dims), _f4(self.vs),
+                                                       _ptr(self.table), self.H, _ptr(self.sorted_pts),
+                                                       _ptr(self.sorted_idx), _ptr(self.counters), _ptr(self.occ),
+                                                       self.occ_bits, _ptr(ws), wb), "pcs_hash_build_sorted")
+                else:
+                    _lib.check(L.pcs_hash_build(s, _ptr(self.ref), self.n, self.seg_div, self.n_seg,
+                                                _ptr(self.seg_lo), _ptr(self.seg_dims), _f4(self.vs), _ptr(self.table),
+                                                self.H, _ptr(self.sorted_pts), _ptr(self.sorted_idx),
+                                                _ptr(self.counters), _ptr(self.occ), self.occ_bits), "pcs_hash_build")
 
     def check(self):
         """Synchronising check of the device-side error flag (table full / key overflow)."""
@@ -307,6 +318,8 @@ def compact_grid(points, voxel_size, **kw):
     grid is rebuilt with the always-sufficient default size.  Costs one host sync."""
     n = points.shape[0]
     small = next_pow2(max(n // 4, 1024))
+    if GRID_SORTED:
+        kw = dict(kw, sorted_cells=True)
     grid = CellGrid(points, voxel_size, table_size=small, **kw)
     if grid.counters[2].item() != 0:
         grid = CellGrid(points, voxel_size, **kw)
