@@ -254,6 +254,102 @@ int pcs_gather_rows(pcs_stream_t s, const void *src, const int64_t *idx, int64_t
 int pcs_group_minmax(pcs_stream_t s, const float *values, int64_t stride, const int64_t *ids, int64_t n, int64_t C,
                      uint32_t *tmp, float *out_min, float *out_max);
 
+
+/* ---- batched cluster tracker ---------------------------------------------------------------------
+ * Replaces the anchor / key / target-frame loops of ClusterTracking.forward and track_frame
+ * (pcdet/models/registration/preprocessors/cluster_tracking.py:430-787, 853-884) together with sample_frame
+ * (:39-51), register_to_next_frame (registration_utils.py:83-206), smooth_velo (:162-199) and the nn_graph
+ * extraction (:710-721).  All (anchor frame, component key) "instances" of a sequence advance together: tracking
+ * step t in [1, 16] moves every anchor a to frame a - t (t <= 8) or a + (t - 8); no host synchronisation between
+ * steps.  The descriptor structs below hold device pointers and scalars only; every field is 8 bytes wide
+ * (pointer, int64_t or double) so that any FFI can fill them without caring about padding.
+ *
+ * Cell grids of the tracker: 16-byte pcs_slot_t tables over packed keys (group << 48 | cx << 32 | cy << 16 | cz),
+ * cell = floor((p - lo) / cs) with one sequence-global origin lo; group = instance (moving side) or frame
+ * (reference side).  Rows are float4 (payload bits, x, y, z). */
+typedef struct {
+  const void *pts;   /* float4[n] (., x, y, z) */
+  const void *group; /* int32[n] instance / frame of every point, < 32768 */
+  const void *skey;  /* int32[n] sort key (component id, ascending == ascending reference id) or NULL: sort by group */
+  const void *bits;  /* uint8[n] up to three flag bits (`stationary` per component key) or NULL */
+  const void *act;   /* int32[n_groups] or NULL: groups with act == 0 are skipped */
+  int64_t n, n_groups, n_keys, ns_only; /* ns_only: voxels whose flag bit 0 wins the majority vote are dropped */
+  double size[3];    /* voxel size (GridSampling3D grid_size) */
+  void *sb;          /* uint32[n_groups][6] bounds of the groups' points (pcs_trk_group_bounds); reset on return */
+  void *table;       /* 16-byte slots [H] (pcs_trk_sampler_init) */
+  int64_t H;
+  void *vsum, *vbits, *vk, *vres; /* double[H][3], int32[H][3], int32[H][2], int32[H][2] */
+  void *pnext, *vlist;            /* int32[n] each */
+  void *ctr;                      /* int32[4]: [0] voxels, [1] voxels kept, [2] sticky error flag */
+  void *kcount, *koff, *kcur;     /* int32[n_keys + 1] each; koff = first output row of every sort key */
+  void *vdeg;                     /* int32[n_keys] += voxels per sort key (dropped ones included), or NULL */
+  void *out_pts, *out_key, *out_group; /* float4[n] (flag bits, mean x, y, z), int32[n], int32[n]; grouped by sort key */
+} pcs_trk_sampler_t;
+
+typedef struct {
+  int64_t J, G;
+  const void *act, *ref_group, *skipmask; /* int32[J]: participates, group of its reference voxels, flag mask skipped */
+  const void *ref_off;                    /* int32[n_groups + 1] rows of every group in ref_pts */
+  const void *g_inst;                     /* int32[G] instance of every component (components grouped by instance) */
+  void *ref_table; int64_t ref_H; void *ref_pts; /* static reference grid; ref_pts float4[.] sorted by cell key */
+  void *mov_table; int64_t mov_H; void *mov_sorted, *mov_sidx, *mov_cells, *mov_ctr; /* moving grid scratch */
+  void *mv; const void *mv_gid, *mv_inst, *n_mv; /* moving voxels float4[.] (in place), component, instance, count */
+  const void *vdeg;                       /* int32[G] voxels per component (matched-fraction denominator) */
+  double lo[3], cs;                       /* grid origin and cell size (>= 1.001 * 3-D radius) */
+  double radius; int64_t df; double angle_reg; int64_t max_iter; double stopping_delta;
+  int64_t want_l1, want_ratio;
+  void *nn_fwd, *nn_bwd, *boff;           /* int32[cap mv], int32[cap backward items], int32[J + 1] */
+  void *mom, *Ti, *T, *mu, *l1_sum, *l1_n; /* double [G][17], [G][12], [G][12] (out), [G][6], [G][2], [G] */
+  void *phase, *cd, *iters, *itcnt;       /* int32[J] x3 (iters = iterations run, out), int32[(max_iter + 2) * 2] */
+  void *last, *loss;                      /* double[J] */
+  void *match_cnt;                        /* int32[G] */
+  void *l1_err, *ratio;                   /* double[G], float[G] outputs (want_l1 / want_ratio) */
+} pcs_trk_icp_t;
+
+typedef struct {
+  int64_t J, G, M, F;
+  const void *inst_anchor, *inst_key, *inst_C, *inst_fmin, *inst_fmax, *inst_has_valid, *inst_goff; /* int32[J(+1)] */
+  const void *seq_sorted, *frame_off;     /* float4[N] points sorted by frame, int32[F + 1] */
+  void *mp; const void *mp0; void *m_last; const void *m_gid, *m_inst; /* moving points grouped by component */
+  const void *g_inst, *g_deg, *g_diam, *g_valid; /* int32, int32, float, uint8 [G] */
+  void *g_stopped, *g_moving, *g_final, *g_minf, *g_maxf; /* uint8 x3, int32 x2 [G] */
+  void *transforms;                       /* double[G][17][12] (R row-major, t), identity on entry */
+  void *velos, *velos_b, *centers, *diffs; /* float[G][17][3] */
+  void *cv_pre, *g_delta, *adam_m, *adam_v; /* float[G][3] x2, float[G][16] x2 */
+  void *csum, *vsum, *l1_err, *ratio, *T; /* double[G][3] x2 (zero), double[G], float[G], double[G][12] */
+  void *vdeg;                             /* int32[G] (zero) */
+  void *cur_act, *cur_nxt, *cur_rel, *cur_haslv, *anyns; /* int32[J] x4, int32[17][J] (zero) */
+  void *sb;                               /* uint32[J][6] (pcs_trk_bounds_reset) */
+  double reg_error_coeff, angle_threshold; int64_t min_move_frame;
+  double radius[8], voxel_size[24];       /* per registration level */
+  double lo[3], nn_radius;
+  void *eg_table; int64_t eg_H; void *eg_sorted, *eg_sidx, *eg_cells, *eg_ctr; /* extraction grid scratch */
+  void *eoff; const void *exoff; void *ex; /* int32[J + 1], int64[J * 17 + 1], int32[exoff[J * 17]] (filled with -1) */
+} pcs_trk_ctx_t;
+
+int pcs_trk_cell_keys(pcs_stream_t s, const float *pts, const int32_t *group, int64_t n, const double *lo, double cs,
+                      int64_t *keys);
+/* table <- n unique cells (key, first row, rows) of a key-sorted row array; H power of two >= 2 n; err int32[1]. */
+int pcs_trk_grid_fill(pcs_stream_t s, pcs_slot_t *table, int64_t H, const int64_t *keys, const int32_t *starts,
+                      const int32_t *counts, int64_t n, int32_t *err);
+int pcs_trk_table_clear(pcs_stream_t s, pcs_slot_t *table, int64_t H, int32_t *ctr /* int32[4] zeroed, or NULL */);
+int pcs_trk_bounds_reset(pcs_stream_t s, uint32_t *sb, int n_groups);
+int pcs_trk_group_bounds(pcs_stream_t s, const float *pts, const int32_t *group, int64_t n, uint32_t *sb);
+int pcs_trk_sampler_init(pcs_stream_t s, const pcs_trk_sampler_t *S);
+/* sample_frame for all groups at once: per-group origin = min of its points, cell = trunc((p - origin) / size),
+ * per voxel fp64 mean, majority vote per flag bit, upper-median sort key. */
+int pcs_trk_sample(pcs_stream_t s, const pcs_trk_sampler_t *S);
+/* register_to_next_frame for all instances in one persistent cooperative launch. */
+int pcs_trk_icp(pcs_stream_t s, const pcs_trk_icp_t *P);
+int pcs_trk_dir_init(pcs_stream_t s, const pcs_trk_ctx_t *C);
+int pcs_trk_step(pcs_stream_t s, const pcs_trk_ctx_t *C, const pcs_trk_sampler_t *S, const pcs_trk_icp_t *levels,
+                 int n_levels, int t);
+/* final component filter + anchor-frame rows of the extraction table; m_frow int32[M] = row of the point in its frame */
+int pcs_trk_finish(pcs_stream_t s, const pcs_trk_ctx_t *C, const int32_t *m_frow);
+/* steps 1..16 and pcs_trk_finish */
+int pcs_trk_run(pcs_stream_t s, const pcs_trk_ctx_t *C, const pcs_trk_sampler_t *S, const pcs_trk_icp_t *levels,
+                int n_levels, const int32_t *m_frow);
+
 #ifdef __cplusplus
 }
 #endif

@@ -70,6 +70,18 @@ _SIGNATURES = {
     "pcs_gather_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "pcs_group_median": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p,
                                  c_void_p]),
+    "pcs_trk_cell_keys": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_double, c_void_p]),
+    "pcs_trk_grid_fill": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "pcs_trk_table_clear": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "pcs_trk_bounds_reset": (c_int, [c_void_p, c_void_p, c_int]),
+    "pcs_trk_group_bounds": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "pcs_trk_sampler_init": (c_int, [c_void_p, c_void_p]),
+    "pcs_trk_sample": (c_int, [c_void_p, c_void_p]),
+    "pcs_trk_icp": (c_int, [c_void_p, c_void_p]),
+    "pcs_trk_dir_init": (c_int, [c_void_p, c_void_p]),
+    "pcs_trk_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int]),
+    "pcs_trk_finish": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "pcs_trk_run": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
 }
 
 

@@ -138,6 +138,9 @@ class ClusterTracking(nn.Module):
         self.min_move_frame = params.get("MIN_MOVE_FRAME", 6)
         self.component_keys = model_cfg["COMPONENT_KEYS"]
         self.verbose = model_cfg.get("VERBOSE", True)
+        # BATCHED (default): all (component key, anchor) pairs advance together on the device (tracker.TrackBatch);
+        # False runs the reference's one-pair-at-a-time control flow (kept for the parity tests)
+        self.batched = bool(model_cfg.get("BATCHED", True))
 
     def format_boxes(self, seq_dict, num_frames):
         return EasyDict(dict(attr=seq_dict["gt_box_attr"].reshape(-1, 7),
@@ -378,25 +381,42 @@ class ClusterTracking(nn.Module):
             return seq_dict
         seq_boxes.best_iou = torch.zeros_like(seq_boxes.attr[:, 0])
         results = {}
-        for comp_key in self.component_keys:
-            seq_points.component = seq_dict[f"point_{comp_key}"]
-            diam = component_diameter(seq_points)[seq_points.component]
-            seq_points.component_diameter = diam
-            seq_points.stationary = diam > STATIONARY_DIAMETER
-            seq_points.extracted = torch.zeros_like(seq_points.fxyz[:, 0]).bool()
-            for frame_id in range(0, num_frames, self.track_interval):
-                frame_mask = (seq_points.fxyz[:, 0] == frame_id).reshape(-1)
-                if not bool(frame_mask.any()):
-                    continue
-                frame_points = EasyDict(filter_dict(seq_points, frame_mask))
-                frame_points.component = frame_points.component - frame_points.component.min()
-                with Timer(f"Tracking Frame {frame_id}", verbose=self.verbose):
-                    extracted = self.track_frame(seq_points, frame_points, seq_boxes)
-                if extracted.fxyz.shape[0] > 0:
-                    extracted, seq_boxes = self.extract_traces_and_update_boxes(all_points, extracted, seq_boxes)
-                if save:
-                    torch.save(extracted, f"{outfolder}/{frame_id:03d}_{comp_key}.pth")
-                results[f"{frame_id:03d}_{comp_key}"] = extracted
+        if self.batched:
+            from ..tracker import TrackBatch
+            comps = [seq_dict[f"point_{k}"] for k in self.component_keys]
+            tb = TrackBatch(seq_points.fxyz, seq_points.frame, comps, self.model_cfg, num_frames=num_frames).run()
+            per_inst = tb.results(seg_label=seq_points.get("segmentation_label"))
+            tb.check()
+            for ki, comp_key in enumerate(self.component_keys):
+                for frame_id in tb.anchors:
+                    j, extracted = per_inst[(ki, frame_id)]
+                    extracted.transforms = tb.transforms(j)
+                    if extracted.fxyz.shape[0] > 0:
+                        extracted, seq_boxes = self.extract_traces_and_update_boxes(all_points, extracted, seq_boxes)
+                    if save:
+                        torch.save(extracted, f"{outfolder}/{frame_id:03d}_{comp_key}.pth")
+                    results[f"{frame_id:03d}_{comp_key}"] = extracted
+            seq_dict["tracking_batch"] = tb
+        else:
+            for comp_key in self.component_keys:
+                seq_points.component = seq_dict[f"point_{comp_key}"]
+                diam = component_diameter(seq_points)[seq_points.component]
+                seq_points.component_diameter = diam
+                seq_points.stationary = diam > STATIONARY_DIAMETER
+                seq_points.extracted = torch.zeros_like(seq_points.fxyz[:, 0]).bool()
+                for frame_id in range(0, num_frames, self.track_interval):
+                    frame_mask = (seq_points.fxyz[:, 0] == frame_id).reshape(-1)
+                    if not bool(frame_mask.any()):
+                        continue
+                    frame_points = EasyDict(filter_dict(seq_points, frame_mask))
+                    frame_points.component = frame_points.component - frame_points.component.min()
+                    with Timer(f"Tracking Frame {frame_id}", verbose=self.verbose):
+                        extracted = self.track_frame(seq_points, frame_points, seq_boxes)
+                    if extracted.fxyz.shape[0] > 0:
+                        extracted, seq_boxes = self.extract_traces_and_update_boxes(all_points, extracted, seq_boxes)
+                    if save:
+                        torch.save(extracted, f"{outfolder}/{frame_id:03d}_{comp_key}.pth")
+                    results[f"{frame_id:03d}_{comp_key}"] = extracted
         if save:
             torch.save(seq_boxes, outpath)
         seq_dict["tracking_results"] = results
