@@ -350,6 +350,33 @@ int pcs_trk_finish(pcs_stream_t s, const pcs_trk_ctx_t *C, const int32_t *m_frow
 int pcs_trk_run(pcs_stream_t s, const pcs_trk_ctx_t *C, const pcs_trk_sampler_t *S, const pcs_trk_icp_t *levels,
                 int n_levels, const int32_t *m_frow);
 
+
+/* Grid over n rows float4 (., x, y, z) tagged with group[n] (< 32768).  table: 16-byte slots [H >= n, power of two]
+ * cleared by the call; sorted float4[n], sidx int32[n], cells int32[n], ctr int32[4] scratch. */
+int pcs_trk_group_grid(pcs_stream_t s, const float *pts, const int32_t *group, int64_t n, const double *lo, double cs,
+                       pcs_slot_t *table, int64_t H, float *sorted, int32_t *sidx, int32_t *cells, int32_t *ctr);
+/* Nearest grid row (index into the pts given to pcs_trk_group_grid, or -1) within `radius` (d2 <= r*r, fp32 FMA order
+ * of the reference) for the queries of nseg segments: segment k covers queries[seg_qstart[k] ...] with
+ * seg_off[k + 1] - seg_off[k] rows and searches group seg_group[k]; out int32[seg_off[nseg]].  Replaces the per-frame
+ * nn_graph calls of extract_traces_and_update_boxes (cluster_tracking.py:356-358). */
+int pcs_trk_group_nn(pcs_stream_t s, const pcs_slot_t *table, int64_t H, const float *sorted, const int32_t *sidx,
+                     const double *lo, double cs, const float *queries, const int32_t *seg_qstart,
+                     const int32_t *seg_off, const int32_t *seg_group, int nseg, float radius, int32_t *out);
+
+/* ---- GT evaluation -------------------------------------------------------------------------------
+ * Replaces points_in_boxes_cpu (pcdet/ops/roiaware_pool3d/src/roiaware_pool3d.cpp:121-168) and the per-component
+ * loops around it (cluster_proposal.py:90-114, 206-255; cluster_tracking.py:340-411).
+ * pcs_box_prep: boxes float[B][7] (x, y, z, dx, dy, dz, heading), sorted by frame -> recs (48 bytes per box).
+ * pcs_points_in_boxes: item i is point pts[sel ? sel[i] : i] (float4, column 0 = frame); it is tested against the
+ * boxes box_off[f] .. box_off[f + 1] of its frame.  first_out[i] = frame-local index of the first box holding it
+ * (-1: none); for every box holding it, cnt_k[cid_k[i] * Bmax + local index] += 1 (k = 0..2, optional).
+ * err int32[1] is set when a frame has more than Bmax boxes. */
+int pcs_box_prep(pcs_stream_t s, const float *boxes, int64_t B, void *recs);
+int pcs_points_in_boxes(pcs_stream_t s, const float *pts, const int32_t *sel, int64_t n, const void *recs,
+                        const int32_t *box_off, int F, int Bmax, const int64_t *cid0, const int64_t *cid1,
+                        const int64_t *cid2, int32_t *cnt0, int32_t *cnt1, int32_t *cnt2, int32_t *first_out,
+                        int32_t *err);
+
 #ifdef __cplusplus
 }
 #endif

@@ -82,6 +82,13 @@ _SIGNATURES = {
     "pcs_trk_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int]),
     "pcs_trk_finish": (c_int, [c_void_p, c_void_p, c_void_p]),
     "pcs_trk_run": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "pcs_trk_group_grid": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_double, c_void_p, c_int64,
+                                   c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pcs_trk_group_nn": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_double, c_void_p,
+                                 c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p]),
+    "pcs_box_prep": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "pcs_points_in_boxes": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int,
+                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 
 

@@ -1748,3 +1748,85 @@ int pcs_trk_run(pcs_stream_t s, const pcs_trk_ctx_t *C, const pcs_trk_sampler_t 
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// generic grouped nearest-neighbour query (extract_traces_and_update_boxes, cluster_tracking.py:356-358): a grid over
+// rows tagged with a group id, queried by segments of a (frame-sorted) point array, one group per segment
+// ---------------------------------------------------------------------------------------------------------------
+namespace pcs {
+
+__global__ void __launch_bounds__(256) trk_gcount_kernel(PGrid g, const float4 *__restrict__ pts,
+                                                         const int *__restrict__ group, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = pts[i];
+  pg_count(g, group[i], p.y, p.z, p.w);
+}
+
+__global__ void __launch_bounds__(256) trk_granges_kernel(PGrid g) {
+  pg_ranges(g, (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x);
+}
+
+__global__ void __launch_bounds__(256) trk_gscatter_kernel(PGrid g, const float4 *__restrict__ pts,
+                                                           const int *__restrict__ group, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = pts[i];
+  pg_scatter(g, group[i], p.y, p.z, p.w, 0u, i);
+}
+
+__global__ void __launch_bounds__(256) trk_gsearch_kernel(PGrid g, const float4 *__restrict__ queries,
+                                                          const int *__restrict__ seg_qstart,
+                                                          const int *__restrict__ seg_off,
+                                                          const int *__restrict__ seg_group, int nseg, float r2,
+                                                          int *__restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int total = seg_off[nseg];
+  for (long long w = warp_id; w < total; w += nwarps) {
+    const int sg = seg_of_item(seg_off, nseg, (int)w);
+    const float4 q = queries[seg_qstart[sg] + ((int)w - seg_off[sg])];
+    const int r = nn_search(g, true, seg_group[sg], q.y, q.z, q.w, 0.f, r2, 0u, lane);
+    if (lane == 0) out[w] = r;
+  }
+}
+
+}  // namespace pcs
+
+extern "C" {
+
+/* Grid over n rows float4 (., x, y, z) tagged with group[n] (< 32768).  table: 16-byte slots [H] cleared by the
+ * call; sorted float4[n], sidx int32[n], cells int32[n], ctr int32[4] scratch. */
+int pcs_trk_group_grid(pcs_stream_t s, const float *pts, const int32_t *group, int64_t n, const double *lo, double cs,
+                       pcs_slot_t *table, int64_t H, float *sorted, int32_t *sidx, int32_t *cells, int32_t *ctr) {
+  if (n < 0 || n >= (1LL << 31) || !lo || cs <= 0.0 || !table || H < 2 || (H & (H - 1)) || H < n || !ctr ||
+      (n > 0 && (!pts || !group || !sorted || !sidx || !cells)) || ((uintptr_t)pts & 15) || ((uintptr_t)sorted & 15))
+    return set_error(PCS_ERR_BAD_ARG, "pcs_trk_group_grid: bad args");
+  cudaStream_t st = as_stream(s);
+  PGrid g = make_pgrid(table, H, sorted, sidx, cells, ctr, lo, cs);
+  PCS_LAUNCH(trk_table_clear_kernel, grid_for(H, 256, 8), 256, 0, st, (int4 *)table, (long long)H, ctr);
+  if (n == 0) return 0;
+  PCS_LAUNCH(trk_gcount_kernel, blocks_for(n, 256), 256, 0, st, g, (const float4 *)pts, group, (int)n);
+  PCS_LAUNCH(trk_granges_kernel, grid_for(n, 256, 4), 256, 0, st, g);
+  PCS_LAUNCH(trk_gscatter_kernel, blocks_for(n, 256), 256, 0, st, g, (const float4 *)pts, group, (int)n);
+  return 0;
+}
+
+/* Nearest grid row (index into the pts given to pcs_trk_group_grid, or -1) within `radius` (3-D, d2 <= r*r in the
+ * reference's fp32 FMA order) for the queries of nseg segments: segment k covers queries[seg_qstart[k] ...] with
+ * seg_off[k + 1] - seg_off[k] rows and searches group seg_group[k]; out int32[seg_off[nseg]]. */
+int pcs_trk_group_nn(pcs_stream_t s, const pcs_slot_t *table, int64_t H, const float *sorted, const int32_t *sidx,
+                     const double *lo, double cs, const float *queries, const int32_t *seg_qstart,
+                     const int32_t *seg_off, const int32_t *seg_group, int nseg, float radius, int32_t *out) {
+  if (!table || H < 2 || (H & (H - 1)) || !lo || cs <= 0.0 || nseg < 0 || ((uintptr_t)queries & 15) ||
+      ((uintptr_t)sorted & 15) || (nseg > 0 && (!queries || !seg_qstart || !seg_off || !seg_group || !out)))
+    return set_error(PCS_ERR_BAD_ARG, "pcs_trk_group_nn: bad args");
+  if (nseg == 0) return 0;
+  PGrid g = make_pgrid((void *)table, H, (void *)sorted, (void *)sidx, nullptr, nullptr, lo, cs);
+  PCS_LAUNCH(trk_gsearch_kernel, 148 * 8, 256, 0, as_stream(s), g, (const float4 *)queries, seg_qstart, seg_off,
+             seg_group, nseg, radius * radius, out);
+  return 0;
+}
+
+}  // extern "C"

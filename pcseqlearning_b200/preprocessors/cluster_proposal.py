@@ -4,14 +4,12 @@ propose_cluster runs, per radius, ONE voxel-hash build and ONE fused search + un
 whole sequence; the reference's 10-frame chunks become key segments of that launch, so the grids, the
 neighbour sets and the chunk-wise component numbering (running offset, cluster_proposal.py:63-81) are the
 same as the reference's per-chunk calls."""
-from collections import defaultdict
-
 import torch
 from torch import nn
 
 from .. import graph_utils, ops
-from ..utils import EasyDict, Timer, filter_dict
-from .eval_utils import points_in_boxes
+from ..utils import EasyDict, Timer
+from .eval_utils import FrameBoxes
 
 CHUNK_FRAMES = 10  # cluster_proposal.py:63
 
@@ -61,88 +59,72 @@ class ClusterProposal(nn.Module):
                              frame=seq_dict["gt_box_frame"].reshape(-1),
                              trace_id=seq_dict["gt_box_track_label"].reshape(-1)))
 
-    def assign_instances_to_boxes(self, point_instance_label, bp_mask):
-        """Majority box of every instance (cluster_proposal.py:90-114), vectorised: one [B, I] count matrix."""
-        uniq, inst = torch.unique(point_instance_label, return_inverse=True)
-        counts = torch.zeros(bp_mask.shape[0], uniq.shape[0], dtype=torch.long, device=bp_mask.device)
-        counts.index_add_(1, inst, bp_mask.long())
-        has = counts.sum(0) > 0
-        box_of = counts.argmax(0)
-        box_of[~has] = -1
-        instance2box = defaultdict(lambda: -1)
-        for k, b in zip(uniq.tolist(), box_of.tolist()):
-            if b >= 0:
-                instance2box[k] = b
-        return instance2box, box_of[inst], uniq, box_of, inst
-
     def evaluate_proposal(self, seq_dict):
         """Point-wise IoU of proposed clusters against GT boxes; emits point_gt_box_id etc. which
-        ClusterTracking requires (cluster_tracking.py:800)."""
-        num_frames = int(seq_dict["point_sweep"].max().long().item()) + 1
+        ClusterTracking requires (cluster_tracking.py:800).
+
+        The reference loops over component keys x frames x components with a CPU point-in-box test per frame
+        (cluster_proposal.py:142-285).  A component lives in exactly one frame, so the whole sequence is evaluated at
+        once: one pcs_points_in_boxes launch gives every point its first box and the (component, box) membership
+        counts of all keys; the majority box, the IoU and the per-box / per-trace maxima are segment reductions."""
+        fxyz = seq_dict["point_fxyz"]
+        num_points = fxyz.shape[0]
+        num_frames = int(seq_dict["num_frames"]) if "num_frames" in seq_dict else \
+            int(seq_dict["point_sweep"].max().long().item()) + 1
         seq_boxes = self.format_boxes(seq_dict, num_frames)
         num_boxes = seq_boxes.attr.shape[0]
-        num_points = seq_dict[f"point_{self.component_keys[0]}"].numel()
         if num_boxes == 0:
             for key in ["gt_box_id", "gt_trace_id", "pred_trace_id", "pred_box_id"]:
                 seq_dict[f"point_{key}"] = seq_dict["segmentation_label"].new_zeros(num_points) - 1
             return seq_dict
-        seq_boxes.best_iou = torch.zeros_like(seq_boxes.attr[:, 0])
-        num_traces = int(seq_boxes.trace_id.max().long().item()) + 1
-        traces = EasyDict(dict(best_iou=seq_boxes.attr.new_zeros(num_traces),
-                               min_frame=seq_boxes.trace_id.new_zeros(num_traces),
-                               max_frame=seq_boxes.trace_id.new_zeros(num_traces)))
-        big = num_frames + 1
-        traces.min_frame = torch.full_like(traces.min_frame, big).scatter_reduce_(
-            0, seq_boxes.trace_id.long(), seq_boxes.frame.long(), "amin")
-        traces.max_frame = torch.zeros_like(traces.max_frame).scatter_reduce_(
-            0, seq_boxes.trace_id.long(), seq_boxes.frame.long(), "amax")
-        fxyz = seq_dict["point_fxyz"]
-        frame_of_point = fxyz[:, 0].round().long()
-        seq_points = None
-        for comp_key in self.component_keys:
-            seq_points = EasyDict(component=seq_dict[f"point_{comp_key}"])
-            for key in ["gt_box_id", "pred_box_id", "gt_trace_id", "pred_trace_id"]:
-                seq_points[key] = torch.zeros_like(seq_points.component) - 1
-            for frame_id in range(num_frames):
-                frame_mask = frame_of_point == frame_id
-                frame_box_mask = (seq_boxes.frame == frame_id).reshape(-1)
-                if not frame_mask.any() or not frame_box_mask.any():
-                    continue
-                comp = seq_points.component[frame_mask]
-                boxes = EasyDict(filter_dict(seq_boxes, frame_box_mask))
-                bp_mask = points_in_boxes(fxyz[frame_mask, 1:], boxes.attr)  # [B, n] int
-                in_box = (bp_mask == 1).any(0)
-                gt_box_id = torch.zeros_like(comp) - 1
-                gt_box_id[in_box] = bp_mask[:, in_box].argmax(0)
-                gt_trace_id = torch.zeros_like(comp) - 1
-                gt_trace_id[in_box] = boxes.trace_id[gt_box_id[in_box]].to(gt_trace_id)
-                _, pred_box_id, uniq, box_of, inst = self.assign_instances_to_boxes(comp, bp_mask)
-                pred_trace_id = torch.zeros_like(comp) - 1
-                valid = pred_box_id >= 0
-                pred_trace_id[valid] = boxes.trace_id[pred_box_id[valid]].to(pred_trace_id)
-                # IoU of every (component, assigned box) pair, all at once (cluster_proposal.py:237-255)
-                sel = box_of >= 0
-                if sel.any():
-                    comp_size = torch.bincount(inst, minlength=uniq.shape[0])
-                    gt_size = torch.bincount(gt_box_id[gt_box_id >= 0], minlength=bp_mask.shape[0])
-                    # intersection = points of the component whose gt_box_id is the assigned box
-                    hit = (gt_box_id == box_of[inst]) & (box_of[inst] >= 0)
-                    inter = torch.bincount(inst[hit], minlength=uniq.shape[0]).float()
-                    union = (comp_size + gt_size[box_of.clamp(min=0)]).float() - inter
-                    iou = torch.where(sel, inter / (union + 1e-6), torch.zeros_like(inter))
-                    best = boxes.best_iou.clone()
-                    best.scatter_reduce_(0, box_of[sel], iou[sel].to(best), "amax")
-                    seq_boxes.best_iou[frame_box_mask] = best
-                    tr = boxes.trace_id[box_of[sel]].long()
-                    traces.best_iou.scatter_reduce_(0, tr, iou[sel].to(traces.best_iou), "amax")
-                for key, val in (("gt_box_id", gt_box_id), ("gt_trace_id", gt_trace_id),
-                                 ("pred_trace_id", pred_trace_id), ("pred_box_id", pred_box_id)):
-                    seq_points[key][frame_mask] = val
-            seq_boxes[f"best_iou_after_{comp_key}"] = seq_boxes["best_iou"].clone()
-        seq_dict["gt_box_best_iou"] = seq_boxes.best_iou
-        seq_dict["gt_trace_best_iou"] = traces.best_iou
-        for key in ["gt_box_id", "gt_trace_id", "pred_trace_id", "pred_box_id"]:
-            seq_dict[f"point_{key}"] = seq_points[key]
+        dev = fxyz.device
+        comps = [seq_dict[f"point_{k}"].reshape(-1).long() for k in self.component_keys]
+        sizes = [int(v) for v in torch.stack([c.max() for c in comps]).tolist()]  # one host sync
+        fb = FrameBoxes(seq_boxes.attr, seq_boxes.frame, num_frames)
+        frame_of_point = seq_dict["point_sweep"].reshape(-1).long()
+        best_iou = torch.zeros_like(seq_boxes.attr[:, 0])
+        trace_id = seq_boxes.trace_id.long()
+        num_traces = int(trace_id.max().item()) + 1
+        trace_best = seq_boxes.attr.new_zeros(num_traces)
+        first, counts = [], []
+        for i0 in range(0, len(comps), 3):  # three count tables per launch
+            f, c = fb.query(fxyz, cids=[(cc, sz + 1) for cc, sz in zip(comps[i0:i0 + 3], sizes[i0:i0 + 3])])
+            first, counts = f, counts + c
+        gt_local = first.long()  # frame-local index of the first box holding the point (-1: none)
+        in_box = gt_local >= 0
+        gt_sorted = torch.where(in_box, fb.off[frame_of_point] + gt_local, gt_local)  # row among frame-sorted boxes
+        trace_sorted = trace_id[fb.order]
+        gt_trace = torch.where(in_box, trace_sorted[gt_sorted.clamp(min=0)], gt_local)
+        gt_size = torch.bincount(gt_sorted[in_box], minlength=num_boxes)
+        best_sorted = torch.zeros(num_boxes, dtype=torch.float64, device=dev)
+        trace_best64 = torch.zeros(num_traces, dtype=torch.float64, device=dev)
+        pred_box = pred_trace = None
+        for comp_key, c, cnt in zip(self.component_keys, comps, counts):
+            Ck = cnt.shape[0]
+            has = cnt.sum(1) > 0
+            box_of = cnt.argmax(1)  # first maximum, like bi_mask.sum(-1).argmax()
+            cframe = torch.zeros(Ck, dtype=torch.int64, device=dev).scatter_(0, c, frame_of_point)
+            comp_size = torch.bincount(c, minlength=Ck)
+            hit = in_box & has[c] & (gt_local == box_of[c])
+            inter = torch.bincount(c[hit], minlength=Ck).double()
+            assigned = (fb.off[cframe] + box_of).clamp(max=num_boxes - 1)
+            union = (comp_size + gt_size[assigned]).double() - inter
+            iou = torch.where(has, inter / (union + 1e-6), torch.zeros_like(inter))
+            best_sorted.scatter_reduce_(0, assigned[has], iou[has], "amax")
+            trace_best64.scatter_reduce_(0, trace_sorted[assigned[has]], iou[has], "amax")
+            pred_box = torch.where(has[c], box_of[c], torch.full_like(c, -1))
+            pred_trace = torch.where(has[c], trace_sorted[assigned[c]], torch.full_like(c, -1))
+            after = torch.zeros_like(best_iou)
+            after[fb.order] = best_sorted.to(best_iou)
+            seq_boxes[f"best_iou_after_{comp_key}"] = after
+        best_iou[fb.order] = best_sorted.to(best_iou)
+        seq_dict["gt_box_best_iou"] = best_iou
+        seq_dict["gt_trace_best_iou"] = trace_best64.to(trace_best)
+        seq_dict["point_gt_box_id"] = gt_local.to(comps[-1])
+        seq_dict["point_gt_trace_id"] = gt_trace.to(comps[-1])
+        seq_dict["point_pred_trace_id"] = pred_trace
+        seq_dict["point_pred_box_id"] = pred_box
+        seq_dict["frame_boxes"] = fb
         return seq_dict
 
     def forward(self, seq_dict):

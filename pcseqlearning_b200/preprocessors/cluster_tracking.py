@@ -355,6 +355,159 @@ class ClusterTracking(nn.Module):
         return full, seq_boxes
 
     # ------------------------------------------------------------------------------------------------------
+    def extract_traces_batched(self, tb, all_points, seq_boxes):
+        """extract_traces_and_update_boxes (cluster_tracking.py:287-428) for ALL instances of a TrackBatch at once.
+
+        The reference loops over instances x extracted frames with one nn_graph call, one CPU point-in-box test and a
+        Python loop over components per iteration.  Here one grid holds the extracted points of every (instance,
+        frame) group, one search gives every above-ground point of those frames its nearest extracted point
+        (r = 1.732 * NN_GRAPH.RADIUS), and the gating / IoU bookkeeping are segment reductions over
+        (component, frame) ids.  Returns {instance: full_extracted EasyDict} (instances without extracted points
+        are absent) and updates seq_boxes.best_iou in place."""
+        import ctypes
+        from .. import _lib
+        from ..ops import _ptr, _stream, next_pow2
+        from ..tracker import REL, ANCHOR_REL
+        L = _lib.lib()
+        dev = all_points.fxyz.device
+        fl = tb.flat_results()
+        sb = fl["slot_bounds"]
+        J, G, F = tb.J, tb.G, tb.F
+        n_ext = int(fl.gid.shape[0])
+        out = {}
+        if n_ext == 0:
+            return out
+        # ---- (instance, relative frame) groups of the extracted points -----------------------------------------
+        anchor_of_inst = torch.tensor(tb.inst_anchor_h, device=dev)
+        k_ext = fl.frame - (anchor_of_inst[fl.inst] - ANCHOR_REL)  # relative frame index 0..16, ascending with frame
+        grp_ext = (fl.inst * REL + k_ext).int().contiguous()
+        gs_ext = fl.gid * REL + k_ext  # (component, frame) id
+        GS = G * REL
+        xy = fl.fxyz[:, 1:3]
+        cnt_gs = torch.bincount(gs_ext, minlength=GS).clamp(min=1).float()
+        ctr = torch.zeros(GS, 2, device=dev).index_add_(0, gs_ext, xy) / cnt_gs[:, None]  # robust_mean (:361)
+        diam = torch.zeros(GS, device=dev).scatter_reduce_(0, gs_ext, (xy - ctr[gs_ext]).norm(p=2, dim=-1), "amax",
+                                                           include_self=False)
+        # ---- all above-ground points, grouped by frame --------------------------------------------------------
+        a_frame = all_points.frame.reshape(-1).long()
+        a_order = torch.argsort(a_frame, stable=True)
+        a_sorted = all_points.fxyz[a_order].contiguous()
+        a_off = torch.zeros(F + 1, dtype=torch.int64, device=dev)
+        a_off[1:] = torch.bincount(a_frame, minlength=F).cumsum(0)
+        a_off_h = a_off.tolist()  # host sync
+        # segments: one per (instance, frame) group that holds extracted points, ascending frame inside an instance
+        seg_group, seg_qstart, seg_cnt = [], [], []
+        slot_of_rel = [8 - k if k < 8 else (0 if k == 8 else k) for k in range(REL)]
+        for j in range(J):
+            a = tb.inst_anchor_h[j]
+            for k in range(REL):
+                t = slot_of_rel[k]
+                if sb[j * REL + t + 1] - sb[j * REL + t] == 0:
+                    continue
+                f = a - ANCHOR_REL + k
+                seg_group.append(j * REL + k)
+                seg_qstart.append(a_off_h[f])
+                seg_cnt.append(a_off_h[f + 1] - a_off_h[f])
+        nseg = len(seg_group)
+        seg_off_h = np.zeros(nseg + 1, dtype=np.int64)
+        seg_off_h[1:] = np.cumsum(seg_cnt)
+        total_q = int(seg_off_h[-1])
+        if total_q >= 2 ** 31:
+            raise _lib.PcsError("extract_traces_batched: more than 2^31 queries")
+        seg_group_t = torch.tensor(seg_group, dtype=torch.int32, device=dev)
+        seg_qstart_t = torch.tensor(seg_qstart, dtype=torch.int32, device=dev)
+        seg_off_t = torch.from_numpy(seg_off_h).to(dev)
+        seg_off32 = seg_off_t.int().contiguous()
+        radius = float(np.float32(float(self.nn_graph.radius) * 1.732))  # :356-358
+        cs = radius * 1.001
+        lo = (ctypes.c_double * 3)(*tb.lo)
+        H = next_pow2(max(2 * n_ext, 1024))
+        table = torch.empty(H, 4, dtype=torch.int32, device=dev)
+        g_sorted = torch.empty(n_ext, 4, dtype=torch.float32, device=dev)
+        g_sidx = torch.empty(n_ext, dtype=torch.int32, device=dev)
+        g_cells = torch.empty(n_ext, dtype=torch.int32, device=dev)
+        g_ctr = torch.zeros(4, dtype=torch.int32, device=dev)
+        nn = torch.empty(max(total_q, 1), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            s = _stream()
+            _lib.check(L.pcs_trk_group_grid(s, _ptr(fl.fxyz.contiguous()), _ptr(grp_ext), n_ext, lo, cs, _ptr(table), H,
+                                            _ptr(g_sorted), _ptr(g_sidx), _ptr(g_cells), _ptr(g_ctr)),
+                       "pcs_trk_group_grid")
+            _lib.check(L.pcs_trk_group_nn(s, _ptr(table), H, _ptr(g_sorted), _ptr(g_sidx), lo, cs, _ptr(a_sorted),
+                                          _ptr(seg_qstart_t), _ptr(seg_off32), _ptr(seg_group_t), nseg, radius,
+                                          _ptr(nn)), "pcs_trk_group_nn")
+        nn = nn[:total_q]
+        w = (nn >= 0).nonzero().reshape(-1)  # host sync; ascending (instance, frame, row)
+        e = nn[w].long()  # extracted entry of the hit
+        sg = torch.searchsorted(seg_off_t, w, right=True) - 1
+        i_all = w - seg_off_t[sg]
+        srow = seg_qstart_t.long()[sg] + i_all  # row among the frame-sorted all_points
+        gs = gs_ext[e]
+        ref_xyz = a_sorted[srow]
+        dz = fl.fxyz[e, 3] - ref_xyz[:, 3]
+        ok = (dz < 0.5) & (dz > -0.05)
+        ok &= (ref_xyz[:, 1:3] - ctr[gs]).norm(p=2, dim=-1) < diam[gs] + 0.05  # :365-370
+        e, sg, i_all, srow, gs = e[ok], sg[ok], i_all[ok], srow[ok], gs[ok]
+        rows = a_order[srow]  # rows of all_points
+        inst_k = fl.inst[e]
+        inst_bounds = torch.searchsorted(inst_k, torch.arange(J + 1, device=dev)).tolist()  # host sync
+        full = EasyDict(dict(fxyz=ref_xyz[ok], component=fl.component[e], frame_indices=i_all,
+                             original_indices=rows.reshape(-1, 1), moving=fl.moving[e]))
+        for key in ("segmentation_label", "instance_label"):
+            if f"full_{key}" in all_points:
+                full[key] = all_points[f"full_{key}"][rows]
+        # ---- per-component bookkeeping --------------------------------------------------------------------------
+        fcol = fl.fxyz[:, 0]
+        g_fmin = torch.full((G,), 1e9, device=dev).scatter_reduce_(0, fl.gid, fcol, "amin")
+        g_fmax = torch.full((G,), -1e9, device=dev).scatter_reduce_(0, fl.gid, fcol, "amax")
+        g_has = g_fmax >= g_fmin
+        g_size = torch.where(g_has, (g_fmax.round() - g_fmin.round() + 1), torch.ones_like(g_fmax)).long()  # :295-297
+        g_hit = torch.zeros(G, dtype=torch.long, device=dev)
+        if seq_boxes.attr.shape[0] > 0 and e.numel() > 0:
+            from .eval_utils import FrameBoxes
+            fb = FrameBoxes(seq_boxes.attr, seq_boxes.frame, F)
+            nb = fb.B
+            first_all, _ = fb.query(a_sorted)  # first box of every above-ground point
+            first_all = first_all.long()
+            a_frame_sorted = a_frame[a_order]
+            in_box = first_all >= 0
+            gt_sorted = fb.off[a_frame_sorted] + first_all
+            gt_size = torch.bincount(gt_sorted[in_box], minlength=nb)
+            _, (counts,) = fb.query(a_sorted, sel=srow.int().contiguous(), cids=[(gs, GS)], want_first=False)
+            has = counts.sum(1) > 0
+            box_of = counts.argmax(1)
+            k_gs = torch.arange(GS, device=dev) % REL
+            gid_gs = torch.div(torch.arange(GS, device=dev), REL, rounding_mode="floor")
+            f_gs = (anchor_of_inst[tb.g_inst.long()][gid_gs] - ANCHOR_REL + k_gs).clamp(0, F - 1)
+            assigned = (fb.off[f_gs] + box_of).clamp(max=nb - 1)
+            mask_size = torch.bincount(gs, minlength=GS)
+            hit_pt = has[gs] & (first_all[srow] == box_of[gs])
+            inter = torch.bincount(gs[hit_pt], minlength=GS)
+            union = mask_size + gt_size[assigned] - inter
+            iou = torch.where(has, inter.float() / (union.float() + 1e-6), torch.zeros(GS, device=dev))  # :400-403
+            g_hit = (has & (iou > 0.7)).reshape(G, REL).sum(1)
+            best_sorted = seq_boxes.best_iou[fb.order].clone()
+            best_sorted.scatter_reduce_(0, assigned[has], iou[has].to(best_sorted), "amax")
+            seq_boxes.best_iou[fb.order] = best_sorted
+        for j in range(J):
+            b0, b1 = sb[j * REL], sb[(j + 1) * REL]
+            if b1 == b0:
+                continue
+            i0, i1 = inst_bounds[j], inst_bounds[j + 1]
+            fe = EasyDict({k: v[i0:i1] for k, v in full.items()})
+            g0, g1 = tb.inst_goff_h[j], tb.inst_goff_h[j + 1]
+            loc = tb.g_local[g0:g1]
+            Cx = int(tb.flat_cmax[j]) + 1
+            hit = torch.zeros(Cx, dtype=torch.long, device=dev)
+            size = torch.ones(Cx, dtype=torch.long, device=dev)
+            inr = loc < Cx
+            hit[loc[inr]] = g_hit[g0:g1][inr]
+            size[loc[inr]] = g_size[g0:g1][inr]
+            fe.component_hit, fe.component_size = hit, size
+            out[j] = fe
+        return out
+
+    # ------------------------------------------------------------------------------------------------------
     def forward(self, seq_dict):
         seq_points = EasyDict(fxyz=seq_dict["point_fxyz"], frame=seq_dict["point_sweep"],
                               gt_box_id=seq_dict["point_gt_box_id"])
@@ -387,12 +540,15 @@ class ClusterTracking(nn.Module):
             tb = TrackBatch(seq_points.fxyz, seq_points.frame, comps, self.model_cfg, num_frames=num_frames).run()
             per_inst = tb.results(seg_label=seq_points.get("segmentation_label"))
             tb.check()
+            full = self.extract_traces_batched(tb, all_points, seq_boxes)
+            lazy = self.model_cfg.get("LAZY_TRANSFORMS", False) and not save
             for ki, comp_key in enumerate(self.component_keys):
                 for frame_id in tb.anchors:
                     j, extracted = per_inst[(ki, frame_id)]
-                    extracted.transforms = tb.transforms(j)
-                    if extracted.fxyz.shape[0] > 0:
-                        extracted, seq_boxes = self.extract_traces_and_update_boxes(all_points, extracted, seq_boxes)
+                    if j in full:
+                        extracted = full[j]
+                    if not lazy:  # reference layout f64[C, frames, 4, 4]; the compact form stays in tracking_batch
+                        extracted.transforms = tb.transforms(j)
                     if save:
                         torch.save(extracted, f"{outfolder}/{frame_id:03d}_{comp_key}.pth")
                     results[f"{frame_id:03d}_{comp_key}"] = extracted

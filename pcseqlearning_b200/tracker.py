@@ -434,9 +434,12 @@ class TrackBatch:
             raise _lib.PcsError(f"tracker: device-side error flags (sampler, moving grid, extraction grid) = {bad}")
 
     # ----------------------------------------------------------------------------------------------------------
-    def results(self, seg_label=None):
-        """Per-instance `extracted` dicts in the reference's layout (cluster_tracking.py:727-752): one host sync
-        for the sizes.  Returns {(key index, anchor frame): (instance, EasyDict)}."""
+    def flat_results(self):
+        """All kept (instance, slot, frame row) entries of the extraction table, concatenated in the reference's
+        order (per instance: anchor frame, then the target frames in tracking order, ascending row inside a frame).
+        One host sync (sizes).  Returns an EasyDict of flat tensors plus `slot_bounds` (host list, J * 17 + 1)."""
+        if getattr(self, "_flat", None) is not None:
+            return self._flat
         dev, t = self.dev, self.t
         J = self.J
         ex = t["ex"]
@@ -446,27 +449,36 @@ class TrackBatch:
         idx = keep.nonzero().reshape(-1)
         exoff = t["exoff"]
         slot = torch.searchsorted(exoff, idx, right=True) - 1  # (j * 17 + t)
-        j_of = torch.div(slot, REL, rounding_mode="floor")
         i_in = idx - exoff[slot]
         slot_frame = torch.from_numpy(self.slot_frame.reshape(-1)).to(dev)
         f_of = slot_frame[slot]
         frame_off = t["frame_off"].long()
         rows = self.order[frame_off[f_of] + i_in]
         gid = ex[idx].long()
-        bounds = torch.searchsorted(idx, exoff[torch.arange(0, J * REL + 1, REL, device=dev)]).tolist()  # host sync
+        slot_bounds = torch.searchsorted(idx, exoff).tolist()  # host sync
+        self._flat = EasyDict(dict(gid=gid, rows=rows, frame_rows=i_in, frame=f_of,
+                                   inst=torch.div(slot, REL, rounding_mode="floor"),
+                                   component=self.g_local[gid], moving=t["g_moving"].bool()[gid],
+                                   fxyz=self.fxyz[rows]))
+        self._flat["slot_bounds"] = slot_bounds
+        cmax = torch.full((J,), -1, dtype=torch.long, device=dev).scatter_reduce_(0, self._flat.inst, self._flat.component, "amax")
+        self.flat_cmax = cmax.tolist()
+        return self._flat
+
+    def results(self, seg_label=None):
+        """Per-instance `extracted` dicts in the reference's layout (cluster_tracking.py:727-752).
+        Returns {(key index, anchor frame): (instance, EasyDict)}."""
+        fl = self.flat_results()
+        sb = fl["slot_bounds"]
+        seg = seg_label[fl.rows] if seg_label is not None else None
         out = {}
-        moving = t["g_moving"].bool()
-        comp_local = self.g_local[gid]
-        mv = moving[gid]
-        fx = self.fxyz[rows]
-        seg = seg_label[rows] if seg_label is not None else None
-        for j in range(J):
+        for j in range(self.J):
             a, ki = self.inst_anchor_h[j], self.inst_key_h[j]
-            b0, b1 = bounds[j], bounds[j + 1]
-            r = rows[b0:b1]
-            e = EasyDict(dict(fxyz=fx[b0:b1], component=comp_local[b0:b1], frame_indices=i_in[b0:b1],
-                              original_indices=r, moving=mv[b0:b1], valid_comp_mask=mv[b0:b1],
-                              gt_box_label=torch.zeros_like(comp_local[b0:b1])))
+            b0, b1 = sb[j * REL], sb[(j + 1) * REL]
+            e = EasyDict(dict(fxyz=fl.fxyz[b0:b1], component=fl.component[b0:b1], frame_indices=fl.frame_rows[b0:b1],
+                              original_indices=fl.rows[b0:b1], moving=fl.moving[b0:b1],
+                              valid_comp_mask=fl.moving[b0:b1],
+                              gt_box_label=torch.zeros_like(fl.component[b0:b1])))
             if seg is not None:
                 e["segmentation_label"] = seg[b0:b1]
             out[(ki, a)] = (j, e)

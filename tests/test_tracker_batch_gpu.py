@@ -155,3 +155,115 @@ def test_voxel_sampler_matches_sample_frame():
     _lib.check(L.pcs_trk_sample(s, ctypes.byref(st)), "sample")
     assert int(sp.t["ctr"][1].item()) == V
     assert int(sp.t["ctr"][2].item()) == 0
+
+
+def _small_sequence(frames=17, beams=24, az=600):
+    """A small synthetic sequence pushed through subsample + ground removal + proposals (with GT evaluation)."""
+    from pcseqlearning_b200.config import cluster_tracking_cfg
+    from pcseqlearning_b200.simple_reg import SimpleReg
+    from pcseqlearning_b200.synthetic import generate_sequence
+    dev = torch.device("cuda", 0)
+    batch = generate_sequence(3, num_frames=frames, num_beams=beams, num_azimuth=az, device=dev)
+    cfg = cluster_tracking_cfg(out_dir="/tmp/pcseq_test_out")
+    for p in cfg.PREPROCESSORS:
+        p.VERBOSE = False
+        p.USE_CACHE = False
+        p.LOG_DIR = None
+        p.SAVE = False
+    cfg.SAVE_DIR = None
+    return batch, cfg, dev
+
+
+def test_extract_traces_batched_vs_sequential():
+    """Batched re-association + IoU bookkeeping against the per-instance mirror of the reference loop."""
+    from pcseqlearning_b200.simple_reg import SimpleReg
+    from pcseqlearning_b200.utils import EasyDict
+    batch, cfg, dev = _small_sequence()
+    model = SimpleReg(cfg, {}, None).to(dev)
+    model.train()
+    model(batch)
+    seq = model.forward_dict["sequences"][0]
+    trk = [m for m in model.preprocessors if type(m).__name__ == "ClusterTracking"][0]
+    tb = seq["tracking_batch"]
+    res = seq["tracking_results"]
+    boxes_b = seq["tracking_boxes"]
+    assert len(res) == tb.J
+    # sequential mirror on the same tracked points
+    all_points = EasyDict(fxyz=seq["full_point_fxyz"], frame=seq["full_point_sweep"], height=seq["full_point_height"],
+                          full_instance_label=seq["full_instance_label"],
+                          full_segmentation_label=seq["full_segmentation_label"])
+    keep = seq["full_point_height"] > 0.0
+    all_points = EasyDict({k: v[keep] for k, v in all_points.items()})
+    seq_boxes = trk.format_boxes(seq, tb.F)
+    seq_boxes.best_iou = torch.zeros_like(seq_boxes.attr[:, 0])
+    per_inst = tb.results(seg_label=seq["segmentation_label"])
+    n_checked = 0
+    for (ki, a), (j, ex) in per_inst.items():
+        key = f"{a:03d}_{trk.component_keys[ki]}"
+        got = res[key]
+        if ex.fxyz.shape[0] == 0:
+            continue
+        ex = EasyDict(dict(ex))
+        ex.transforms = tb.transforms(j)
+        want, seq_boxes = trk.extract_traces_and_update_boxes(all_points, ex, seq_boxes)
+        for k in ("fxyz", "component", "frame_indices", "original_indices", "moving", "segmentation_label",
+                  "instance_label", "component_hit", "component_size"):
+            assert torch.equal(got[k], want[k]), (key, k, got[k].shape, want[k].shape)
+        assert torch.equal(got["transforms"], want["transforms"])
+        n_checked += 1
+    assert n_checked > 0
+    assert torch.allclose(boxes_b.best_iou, seq_boxes.best_iou, atol=1e-6)
+    assert float(boxes_b.best_iou.max()) > 0.3
+
+
+def test_evaluate_proposal_vs_oracle_loops():
+    """Sequence-wide evaluate_proposal against a per-frame / per-component restatement of the reference loops
+    (cluster_proposal.py:142-285) built on the oracle's points_in_boxes."""
+    from oracle import cpu_ops as oracle
+    from pcseqlearning_b200.simple_reg import SimpleReg
+    batch, cfg, dev = _small_sequence(frames=6)
+    cfg.PREPROCESSORS = [p for p in cfg.PREPROCESSORS if p.NAME != "ClusterTracking"]
+    model = SimpleReg(cfg, {}, None).to(dev)
+    model.train()
+    model(batch)
+    seq = model.forward_dict["sequences"][0]
+    fxyz = seq["point_fxyz"].cpu().numpy()
+    frame = np.rint(fxyz[:, 0]).astype(np.int64)
+    attr = seq["gt_box_attr"].reshape(-1, 7).cpu().numpy()
+    bframe = seq["gt_box_frame"].reshape(-1).cpu().numpy()
+    trace = seq["gt_box_track_label"].reshape(-1).cpu().numpy()
+    best = np.zeros(attr.shape[0], np.float32)
+    tbest = np.zeros(int(trace.max()) + 1, np.float32)
+    gt_box = np.full(fxyz.shape[0], -1, np.int64)
+    pred_box = None
+    for key in ("component_rad1x25", "component_rad0x75", "component_rad0x25"):
+        comp = seq[f"point_{key}"].cpu().numpy()
+        pred_box = np.full(fxyz.shape[0], -1, np.int64)
+        for f in range(int(frame.max()) + 1):
+            pm, bm = frame == f, bframe == f
+            if not pm.any() or not bm.any():
+                continue
+            bp = oracle.points_in_boxes(np.ascontiguousarray(fxyz[pm, 1:]), np.ascontiguousarray(attr[bm]))
+            inb = (bp == 1).any(0)
+            g = np.full(pm.sum(), -1, np.int64)
+            g[inb] = bp[:, inb].argmax(0)
+            gt_box[pm] = g
+            c_f = comp[pm]
+            pb = np.full(pm.sum(), -1, np.int64)
+            bidx = np.nonzero(bm)[0]
+            for c in np.unique(c_f):
+                cm = c_f == c
+                if not bp[:, cm].any():
+                    continue
+                b = int(bp[:, cm].sum(-1).argmax())
+                pb[cm] = b
+                m1 = g == b
+                iou = float((m1 & cm).sum()) / (float((m1 | cm).sum()) + 1e-6)
+                best[bidx[b]] = max(best[bidx[b]], np.float32(iou))
+                tbest[trace[bidx[b]]] = max(tbest[trace[bidx[b]]], np.float32(iou))
+            pred_box[pm] = pb
+    np.testing.assert_array_equal(seq["point_gt_box_id"].cpu().numpy(), gt_box)
+    np.testing.assert_array_equal(seq["point_pred_box_id"].cpu().numpy(), pred_box)
+    np.testing.assert_allclose(seq["gt_box_best_iou"].cpu().numpy(), best, atol=1e-6)
+    np.testing.assert_allclose(seq["gt_trace_best_iou"].cpu().numpy(), tbest, atol=1e-6)
+    assert best.max() > 0.5
