@@ -288,22 +288,27 @@ typedef struct {
 
 typedef struct {
   int64_t J, G;
-  const void *act, *ref_group, *skipmask; /* int32[J]: participates, group of its reference voxels, flag mask skipped */
+  const void *act, *ref_group, *ref_group_all, *skipmask; /* int32[J]: participates, group of its reference voxels
+                                             (ICP targets / matched-fraction search), flag mask skipped */
   const void *ref_off;                    /* int32[n_groups + 1] rows of every group in ref_pts */
   const void *g_inst;                     /* int32[G] instance of every component (components grouped by instance) */
   void *ref_table; int64_t ref_H; void *ref_pts; /* static reference grid; ref_pts float4[.] sorted by cell key */
   void *mov_table; int64_t mov_H; void *mov_sorted, *mov_sidx, *mov_cells, *mov_ctr; /* moving grid scratch */
   void *mv; const void *mv_gid, *mv_inst, *n_mv; /* moving voxels float4[.] (in place), component, instance, count */
+  int64_t mv_cap;                         /* capacity of the moving voxel arrays (n_mv[0] <= mv_cap) */
   const void *vdeg;                       /* int32[G] voxels per component (matched-fraction denominator) */
-  double lo[3], cs;                       /* grid origin and cell size (>= 1.001 * 3-D radius) */
+  double lo[3], cs;                       /* grid origin and cell size (>= 1.001 * 3-D radius / rings) */
+  int64_t rings;                          /* 1: search 3x3x3 cells, 2: 5x5x5 (cell size = half the radius) */
   double radius; int64_t df; double angle_reg; int64_t max_iter; double stopping_delta;
   int64_t want_l1, want_ratio;
   void *nn_fwd, *nn_bwd, *boff;           /* int32[cap mv], int32[cap backward items], int32[J + 1] */
+  void *mvbeg, *mvend;                    /* int32[J] scratch */
   void *mom, *Ti, *T, *mu, *l1_sum, *l1_n; /* double [G][17], [G][12], [G][12] (out), [G][6], [G][2], [G] */
   void *phase, *cd, *iters, *itcnt;       /* int32[J] x3 (iters = iterations run, out), int32[(max_iter + 2) * 2] */
   void *last, *loss;                      /* double[J] */
   void *match_cnt;                        /* int32[G] */
   void *l1_err, *ratio;                   /* double[G], float[G] outputs (want_l1 / want_ratio) */
+  void *prof;                             /* optional int64[16] += ns per phase (B C D E F G H tail), [8] iterations, [9] launches */
 } pcs_trk_icp_t;
 
 typedef struct {
@@ -318,7 +323,9 @@ typedef struct {
   void *cv_pre, *g_delta, *adam_m, *adam_v; /* float[G][3] x2, float[G][16] x2 */
   void *csum, *vsum, *l1_err, *ratio, *T; /* double[G][3] x2 (zero), double[G], float[G], double[G][12] */
   void *vdeg;                             /* int32[G] (zero) */
-  void *cur_act, *cur_nxt, *cur_rel, *cur_haslv, *anyns; /* int32[J] x4, int32[17][J] (zero) */
+  void *cur_act, *cur_nxt, *cur_rel, *cur_haslv, *cur_grp, *cur_grp_all; /* int32[J] x6 */
+  int64_t n_keys;                         /* component keys: reference group = key * F + frame, all voxels: n_keys * F + frame */
+  void *anyns;                            /* int32[17][J] (zero) */
   void *sb;                               /* uint32[J][6] (pcs_trk_bounds_reset) */
   double reg_error_coeff, angle_threshold; int64_t min_move_frame;
   double radius[8], voxel_size[24];       /* per registration level */

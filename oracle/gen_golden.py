@@ -159,21 +159,6 @@ def gen_registration():
     print("registration.npz", {k: v.shape for k, v in out.items() if k.endswith("_T")})
 
 
-def main():
-    os.makedirs(OUT, exist_ok=True)
-    torch.manual_seed(0)
-    gen_radius_graph()
-    gen_grid_sampling()
-    gen_proposal()
-    gen_registration()
-    gen_ground()
-    gen_tracking()
-
-
-if __name__ == "__main__":
-    main()
-
-
 def gen_ground():
     """ground_plane_removal (preprocessor_utils.py:352-419) with the north-star yaml's GroundPlaneRemover block."""
     pu = R.load("pcdet.models.registration.preprocessors.preprocessor_utils")
@@ -240,3 +225,163 @@ def gen_tracking():
                         ex_moving=ex.moving.numpy(), transforms=ex.transforms.numpy())
     print("tracking.npz", f.shape, "extracted", ex.fxyz.shape, "components kept", ex.component.unique().numel(),
           "transforms", tuple(ex.transforms.shape))
+
+
+def _ref_function(path, name, glb):
+    """Compile ONE function of a reference source file (the module itself may not be importable here) and return
+    it; the code that runs is the reference's, read from /root/reference at generation time."""
+    import ast
+    src = open(os.path.join(R.REF, path)).read()
+    tree = ast.parse(src)
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef) and node.name == name:
+            mod = ast.Module(body=[node], type_ignores=[])
+            code = compile(mod, os.path.join(R.REF, path), "exec")
+            ns = dict(glb)
+            exec(code, ns)
+            return ns[name]
+    raise KeyError(name)
+
+
+def gen_eval_tracking():
+    """GT formatting (simple_reg.py:35-101), ClusterProposal.evaluate_proposal (cluster_proposal.py:142-285), one
+    ClusterTracking.track_frame with every register_to_next_frame call recorded (teacher forcing), and
+    extract_traces_and_update_boxes (cluster_tracking.py:287-428) -- all run by the reference's own code on the CPU."""
+    import time
+    ct = R.load("pcdet.models.registration.preprocessors.cluster_tracking")
+    from easydict import EasyDict  # the shim installed by ref_import
+    cp = R.load("pcdet.models.registration.preprocessors.cluster_proposal")
+    ru = R.load("pcdet.models.registration.preprocessors.registration_utils")
+    cu = R.load("pcdet.utils.common_utils")
+    bu = R.load("pcdet.utils.box_utils")
+    from . import cpu_ops as ops
+    b, f_all, seg_all = _scene(8, 17, 24, 600)
+    inst_all = b["instance_label"]
+    sweep_all = b["point_sweep"]
+    # --- reference GT formatting ------------------------------------------------------------------------------
+    fmt = _ref_function("pcdet/models/registration/simple_reg.py", "format_boxes",
+                        dict(torch=torch, np=np, EasyDict=EasyDict, common_utils=cu, box_utils=bu))
+    seq = EasyDict(dict(point_sweep=sweep_all.clone()))
+    for key in ["gt_box_cls_label", "gt_box_attr", "augmented", "num_points_in_gt", "gt_boxes", "obj_ids",
+                "gt_box_corners_3d"]:
+        seq[key] = b[key][0]
+    seq = fmt(None, seq)
+    box_out = {f"box_{k}": seq[k].numpy() for k in ["gt_box_attr", "gt_box_cls_label", "gt_box_frame",
+                                                    "gt_box_track_label", "gt_box_velo", "moving"]}
+    # --- ground removal by label; a third of the ground points stay "above ground" in the full arrays ----------
+    rng = np.random.default_rng(5)
+    height = torch.where(seg_all < 17, torch.ones(seg_all.shape[0]),
+                         torch.from_numpy(np.where(rng.random(seg_all.shape[0]) < 0.3, 0.05, -0.1)).float())
+    keep = seg_all < 17
+    f, seg, sweep, inst = f_all[keep], seg_all[keep], sweep_all[keep], inst_all[keep]
+    comps = {}
+    for key, r in (("component_rad1x25", 1.25), ("component_rad0x75", 0.75), ("component_rad0x25", 0.25)):
+        comps[key] = torch.from_numpy(ops.propose_clusters(f.numpy(), r)[0])
+    # --- reference evaluate_proposal -------------------------------------------------------------------------
+    seq.update(dict(point_fxyz=f.clone(), point_sweep=sweep.clone(), segmentation_label=seg.clone(),
+                    instance_label=inst.clone(), frame_id=np.array(["seq_golden_000"])))
+    for key, c in comps.items():
+        seq[f"point_{key}"] = c.clone()
+    prop = cp.ClusterProposal.__new__(cp.ClusterProposal)
+    torch.nn.Module.__init__(prop)
+    prop.component_keys = list(comps.keys())
+    prop.model_cfg = EasyDict(dict(DIR=tempfile.mkdtemp()))
+    t0 = time.time()
+    seq = prop.evaluate_proposal(seq)
+    print(f"reference evaluate_proposal took {time.time() - t0:.1f}s")
+    eval_out = {f"eval_{k}": seq[k].numpy() for k in ["gt_box_best_iou", "gt_trace_best_iou", "point_gt_box_id",
+                                                      "point_gt_trace_id", "point_pred_trace_id", "point_pred_box_id"]}
+    # --- reference track_frame with recorded ICP calls -------------------------------------------------------------
+    cfg = R.edict(
+        ANGLE_REGULARIZER=10, COMPONENT_KEYS=["component_rad0x75"],
+        REGISTRATION=dict(GRAPH=dict(TYPE="RadiusGraph", RADIUS=[2.5, 1.25, 1.0], MAX_NUM_NEIGHBORS=1,
+                                     SORT_BY_DIST=True, RELATIVE_KEY="fxyz"),
+                          VOXEL_SIZE=[[0.4, 0.4, 0.6], [0.2, 0.2, 0.3], [0.1, 0.1, 0.15]],
+                          STOPPING_DELTA=[0.05, 0.05, 0.05]),
+        NN_GRAPH=dict(TYPE="RadiusGraph", RADIUS=0.5, MAX_NUM_NEIGHBORS=1, SORT_BY_DIST=True, RELATIVE_KEY="fxyz"),
+        DIR="/tmp/unused",
+        TRACKING_PARAMS=dict(REGISTRATION_ERROR_COEFFICIENT=0.13, TRACK_INTERVAL=8, ANGLE_THRESHOLD=45,
+                             MIN_MOVE_FRAME=6))
+    mod = ct.ClusterTracking(cfg, {})
+    comp = comps["component_rad0x75"]
+    seq_points = R.edict(fxyz=f.clone(), frame=sweep.clone(), gt_box_id=seq["point_gt_box_id"].clone(),
+                         segmentation_label=seg.clone(), instance_label=inst.clone(), component=comp.clone())
+    diam = ct.component_diameter(seq_points)[seq_points.component]
+    seq_points.component_diameter = diam
+    seq_points.stationary = diam > 12.5
+    seq_points.extracted = torch.zeros_like(seq_points.fxyz[:, 0]).bool()
+    anchor = 8
+    frame_mask = (seq_points.fxyz[:, 0] == anchor).reshape(-1)
+    frame_points = R.edict(**cu.filter_dict(seq_points, frame_mask))
+    frame_points.component = frame_points.component - frame_points.component.min()
+    calls = []
+    orig_reg = ct.register_to_next_frame
+
+    def recording_reg(graph, moving, ref, num_components, angle_regularizer=10, max_iter=20, stopping_delta=5e-2):
+        rec = dict(mov=moving.fxyz.clone().numpy(), mov_comp=moving.component.clone().numpy(),
+                   mov_stat=moving.stationary.clone().numpy(), ref=ref.fxyz.clone().numpy(),
+                   ref_stat=ref.stationary.clone().numpy(), radius=float(graph.radius), C=int(num_components),
+                   max_iter=int(max_iter), delta=float(stopping_delta), reg=float(angle_regularizer))
+        out = orig_reg(graph, moving, ref, num_components, angle_regularizer, max_iter, stopping_delta)
+        rec.update(T=out[1].clone().numpy(), l1=out[2].clone().numpy(), ratio=out[3].clone().numpy(),
+                   moved=out[0].fxyz.clone().numpy())
+        calls.append(rec)
+        return out
+
+    ct.register_to_next_frame = recording_reg
+    t0 = time.time()
+    torch.manual_seed(0)
+    seq_boxes = mod.format_boxes(seq, 17)
+    seq_boxes.best_iou = torch.zeros_like(seq_boxes.attr[:, 0])
+    ex = mod.track_frame(seq_points, frame_points, seq_boxes)
+    ct.register_to_next_frame = orig_reg
+    print(f"reference track_frame took {time.time() - t0:.1f}s, {len(calls)} ICP calls")
+    ex_in = {f"ex_{k}": ex[k].numpy() for k in ["fxyz", "component", "segmentation_label", "frame_indices",
+                                                "original_indices", "moving", "transforms"]}
+    # --- reference extract_traces_and_update_boxes --------------------------------------------------------------------
+    all_mask = height > 0
+    all_points = R.edict(fxyz=f_all[all_mask].clone(), frame=sweep_all[all_mask].clone(), height=height[all_mask].clone(),
+                         full_instance_label=inst_all[all_mask].clone(),
+                         full_segmentation_label=seg_all[all_mask].clone())
+    mod.visualize = False
+    t0 = time.time()
+    ex_copy = R.edict(**{k: (v.clone() if torch.is_tensor(v) else v) for k, v in ex.items()})
+    full, seq_boxes = mod.extract_traces_and_update_boxes(all_points, ex_copy, seq_boxes)
+    print(f"reference extract_traces_and_update_boxes took {time.time() - t0:.1f}s")
+    full_out = {f"full_{k}": full[k].numpy() for k in ["fxyz", "component", "segmentation_label", "instance_label",
+                                                       "original_indices", "frame_indices", "moving", "component_hit",
+                                                       "component_size"]}
+    np.savez_compressed(
+        os.path.join(OUT, "eval_tracking.npz"), points_all=f_all.numpy(), sweep_all=sweep_all.numpy(),
+        seg_all=seg_all.numpy(), inst_all=inst_all.numpy(), height_all=height.numpy(),
+        raw_gt_box_attr=b["gt_box_attr"][0].numpy(), raw_gt_box_cls_label=b["gt_box_cls_label"][0].numpy(),
+        raw_obj_ids=np.asarray(b["obj_ids"][0]).astype(str), raw_augmented=b["augmented"][0].numpy(),
+        raw_num_points_in_gt=b["num_points_in_gt"][0].numpy(),
+        comp_rad1x25=comps["component_rad1x25"].numpy(), comp_rad0x75=comps["component_rad0x75"].numpy(),
+        comp_rad0x25=comps["component_rad0x25"].numpy(), anchor=np.array(anchor),
+        best_iou_after_tracking=seq_boxes.best_iou.numpy(), **box_out, **eval_out, **ex_in, **full_out)
+    # teacher-forcing records: a spread of the calls (all three levels, near and far target frames)
+    pick = sorted(set(list(range(0, 6)) + list(range(6, len(calls), max(1, len(calls) // 14)))))[:20]
+    steps = {"n_calls": np.array(len(calls)), "picked": np.array(pick)}
+    for i, ci in enumerate(pick):
+        for k, v in calls[ci].items():
+            steps[f"c{i}_{k}"] = np.asarray(v)
+    np.savez_compressed(os.path.join(OUT, "tracking_steps.npz"), **steps)
+    print("eval_tracking.npz / tracking_steps.npz", f.shape, "extracted", ex.fxyz.shape, "full", full.fxyz.shape,
+          "boxes", seq_boxes.attr.shape, "best_iou max", float(seq_boxes.best_iou.max()), "calls", len(calls), "picked", len(pick))
+
+
+def main():
+    """python -m oracle.gen_golden [name ...]   (default: every fixture)"""
+    import sys
+    os.makedirs(OUT, exist_ok=True)
+    gens = dict(radius_graph=gen_radius_graph, grid_sampling=gen_grid_sampling, proposal=gen_proposal,
+                registration=gen_registration, ground=gen_ground, tracking=gen_tracking,
+                eval_tracking=gen_eval_tracking)
+    for name in (sys.argv[1:] or list(gens)):
+        torch.manual_seed(0)
+        gens[name]()
+
+
+if __name__ == "__main__":
+    main()

@@ -20,6 +20,7 @@
 // cell layout, so cells are keyed (group, cx, cy, cz) with a sequence-global origin; only the distance arithmetic
 // (fp32, FMA chain starting with the frame difference, torch_hash_kernel.cu:364-370) is the reference's.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -149,12 +150,15 @@ __device__ __forceinline__ float dist2_acc(float acc, float rx, float ry, float 
 // payload has a bit of `skipmask` set are ignored.  Returns the row's original index (warp-uniform) or -1; ties by
 // ascending index.
 __device__ int nn_search(const PGrid &g, bool cursor_mode, int group, float qx, float qy, float qz, float acc0,
-                         float r2, unsigned int skipmask, int lane) {
+                         float r2, unsigned int skipmask, int lane, float *d2_out = nullptr,
+                         unsigned long long best0 = ~0ull) {
   const float ux = cell_u(qx, g.lo0, g.inv_cs), uy = cell_u(qy, g.lo1, g.inv_cs), uz = cell_u(qz, g.lo2, g.inv_cs);
   const float fx = floorf(ux), fy = floorf(uy), fz = floorf(uz);
   const int cx = clamp_cell((int)fx), cy = clamp_cell((int)fy), cz = clamp_cell((int)fz);
   int start = 0, count = 0;
   unsigned int sel = 0xffffffffu;
+  // best0: a known candidate (d2 bits << 32 | index) -- its distance prunes the cell lookups from the start
+  if (best0 != ~0ull) r2 = fminf(r2, __uint_as_float((unsigned int)(best0 >> 32)));
   if (lane < 27) {
     const int ox = lane % 3 - 1, oy = (lane / 3) % 3 - 1, oz = lane / 9 - 1;
     const int nx = cx + ox, ny = cy + oy, nz = cz + oz;
@@ -179,7 +183,7 @@ __device__ int nn_search(const PGrid &g, bool cursor_mode, int group, float qx, 
       }
     }
   }
-  unsigned long long best = ~0ull;
+  unsigned long long best = best0;
   float bound = r2;
   while (true) {
     const unsigned int pick = __reduce_min_sync(kAll, sel);
@@ -208,7 +212,137 @@ __device__ int nn_search(const PGrid &g, bool cursor_mode, int group, float qx, 
     if (wb != ~0ull) bound = fminf(bound, __uint_as_float((unsigned int)(wb >> 32)));
   }
   if (best == ~0ull) return -1;
+  if (d2_out) *d2_out = __uint_as_float((unsigned int)(best >> 32));
   return (int)(unsigned int)(best & 0xffffffffu);
+}
+
+// Outer shell of the 5x5x5 block (cells with a coordinate offset of +-2): continues a search started by nn_search on
+// the inner 27 cells when the ball of the current bound sticks out of them.  `best` / `bound` are warp-uniform.
+__device__ void nn_search_shell(const PGrid &g, bool cursor_mode, int group, float qx, float qy, float qz, float acc0,
+                                unsigned int skipmask, int lane, unsigned long long &best, float &bound) {
+  const float ux = cell_u(qx, g.lo0, g.inv_cs), uy = cell_u(qy, g.lo1, g.inv_cs), uz = cell_u(qz, g.lo2, g.inv_cs);
+  const float fx = floorf(ux), fy = floorf(uy), fz = floorf(uz);
+  const int cx = clamp_cell((int)fx), cy = clamp_cell((int)fy), cz = clamp_cell((int)fz);
+  for (int base = 0; base < 125; base += 32) {
+    const int idx = base + lane;
+    int start = 0, count = 0;
+    if (idx < 125) {
+      const int ox = idx % 5 - 2, oy = (idx / 5) % 5 - 2, oz = idx / 25 - 2;
+      const bool outer = ox == 2 || ox == -2 || oy == 2 || oy == -2 || oz == 2 || oz == -2;
+      const int nx = cx + ox, ny = cy + oy, nz = cz + oz;
+      if (outer && nx >= 0 && nx <= 65535 && ny >= 0 && ny <= 65535 && nz >= 0 && nz <= 65535) {
+        float gx = ox == 0 ? 0.f : (ox > 0 ? (fx + (float)ox - ux) : (ux - fx + (float)(-ox - 1)));
+        float gy = oy == 0 ? 0.f : (oy > 0 ? (fy + (float)oy - uy) : (uy - fy + (float)(-oy - 1)));
+        float gz = oz == 0 ? 0.f : (oz > 0 ? (fz + (float)oz - uz) : (uz - fz + (float)(-oz - 1)));
+        gx -= 4e-6f * (fabsf(ux) + 1.f);
+        gy -= 4e-6f * (fabsf(uy) + 1.f);
+        gz -= 4e-6f * (fabsf(uz) + 1.f);
+        gx = (ox != 0 && gx > 0.f) ? gx * g.cs : 0.f;
+        gy = (oy != 0 && gy > 0.f) ? gy * g.cs : 0.f;
+        gz = (oz != 0 && gz > 0.f) ? gz * g.cs : 0.f;
+        const float dmin2 = (gx * gx + gy * gy + gz * gz + acc0) * 0.99999f;
+        if (dmin2 <= bound) {
+          int s = 0, c = 0;
+          if (pg_lookup(g, pkey(group, nx, ny, nz), s, c) && c > 0) {
+            start = cursor_mode ? s - c : s;
+            count = c;
+          }
+        }
+      }
+    }
+    unsigned int todo = __ballot_sync(kAll, count > 0);
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int cs = __shfl_sync(kAll, start, src), cc = __shfl_sync(kAll, count, src);
+      for (int j = lane; j < cc; j += 32) {
+        const float4 p = g.sorted[cs + j];
+        if (__float_as_uint(p.x) & skipmask) continue;
+        const float d2 = dist2_acc(acc0, p.y, p.z, p.w, qx, qy, qz);
+        if (d2 <= bound) {
+          const unsigned int idx2 = g.sidx ? (unsigned int)g.sidx[cs + j] : (unsigned int)(cs + j);
+          const unsigned long long k = ((unsigned long long)__float_as_uint(d2) << 32) | idx2;
+          best = k < best ? k : best;
+        }
+      }
+      unsigned long long wb = best;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long t = __shfl_xor_sync(kAll, wb, o);
+        wb = t < wb ? t : wb;
+      }
+      best = wb;
+      if (wb != ~0ull) bound = fminf(bound, __uint_as_float((unsigned int)(wb >> 32)));
+    }
+  }
+}
+
+// nearest row within the radius over (2 * rings + 1)^3 cells (rings = 1 or 2: cell size >= radius / rings)
+__device__ __forceinline__ int nn_search_rings(const PGrid &g, bool cursor_mode, int group, float qx, float qy, float qz,
+                                               float acc0, float r2, unsigned int skipmask, int lane, int rings,
+                                               unsigned long long best0 = ~0ull) {
+  float d2 = 0.f;
+  int r = nn_search(g, cursor_mode, group, qx, qy, qz, acc0, r2, skipmask, lane, &d2, best0);
+  if (rings < 2) return r;
+  float bound = r >= 0 ? d2 : r2;
+  // everything outside the inner block is farther than one cell (minus the fp32 slack of the cell coordinates)
+  const float cover = 0.98f * g.cs;
+  if (bound - acc0 <= cover * cover) return r;
+  unsigned long long best = r >= 0 ? (((unsigned long long)__float_as_uint(d2) << 32) | (unsigned int)r) : ~0ull;
+  nn_search_shell(g, cursor_mode, group, qx, qy, qz, acc0, skipmask, lane, best, bound);
+  if (best == ~0ull) return -1;
+  return (int)(unsigned int)(best & 0xffffffffu);
+}
+
+// One THREAD searches the inner 27 cells for the row nearest to the query with d2 <= bound.  Exact whenever the ball
+// of `bound` lies inside the 27-cell block, i.e. (bound - acc0) <= (0.98 * cs)^2 -- the caller guarantees it (the
+// bound is the distance to the neighbour of the previous ICP iteration).  Returns (d2 bits << 32 | index) or ~0.
+__device__ unsigned long long nn_search_thread(const PGrid &g, bool cursor_mode, int group, float qx, float qy, float qz,
+                                               float acc0, float bound, unsigned int skipmask) {
+  const float ux = cell_u(qx, g.lo0, g.inv_cs), uy = cell_u(qy, g.lo1, g.inv_cs), uz = cell_u(qz, g.lo2, g.inv_cs);
+  const float fx = floorf(ux), fy = floorf(uy), fz = floorf(uz);
+  const int cx = clamp_cell((int)fx), cy = clamp_cell((int)fy), cz = clamp_cell((int)fz);
+  // per-axis gaps to the lower / upper neighbour cell (metres, conservative)
+  float glo[3], ghi[3];
+  {
+    const float u[3] = {ux, uy, uz}, f[3] = {fx, fy, fz};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const float m = 4e-6f * (fabsf(u[k]) + 1.f);
+      const float a = u[k] - f[k] - m, b = f[k] + 1.f - u[k] - m;
+      glo[k] = a > 0.f ? a * g.cs : 0.f;
+      ghi[k] = b > 0.f ? b * g.cs : 0.f;
+    }
+  }
+  unsigned long long best = ~0ull;
+  for (int i = 0; i < 27; i++) {
+    // own cell first (i = 0), then the others
+    const int t = i == 0 ? 13 : (i <= 13 ? i - 1 : i);
+    const int ox = t % 3 - 1, oy = (t / 3) % 3 - 1, oz = t / 9 - 1;
+    const float gx = ox == 0 ? 0.f : (ox > 0 ? ghi[0] : glo[0]);
+    const float gy = oy == 0 ? 0.f : (oy > 0 ? ghi[1] : glo[1]);
+    const float gz = oz == 0 ? 0.f : (oz > 0 ? ghi[2] : glo[2]);
+    if ((gx * gx + gy * gy + gz * gz + acc0) * 0.99999f > bound) continue;
+    const int nx = cx + ox, ny = cy + oy, nz = cz + oz;
+    if (nx < 0 || nx > 65535 || ny < 0 || ny > 65535 || nz < 0 || nz > 65535) continue;
+    int s = 0, c = 0;
+    if (!pg_lookup(g, pkey(group, nx, ny, nz), s, c) || c <= 0) continue;
+    if (cursor_mode) s -= c;
+    for (int j = 0; j < c; j++) {
+      const float4 p = g.sorted[s + j];
+      if (__float_as_uint(p.x) & skipmask) continue;
+      const float d2 = dist2_acc(acc0, p.y, p.z, p.w, qx, qy, qz);
+      if (d2 <= bound) {
+        const unsigned int idx = g.sidx ? (unsigned int)g.sidx[s + j] : (unsigned int)(s + j);
+        const unsigned long long k = ((unsigned long long)__float_as_uint(d2) << 32) | idx;
+        if (k < best) {
+          best = k;
+          bound = d2;
+        }
+      }
+    }
+  }
+  return best;
 }
 
 // upper_bound(off, n + 1 entries, x) - 1 : the segment that holds item x
@@ -545,7 +679,8 @@ enum { PH_RUN = 0, PH_FINISHING = 1, PH_FROZEN = 2 };
 struct IcpB {
   int J, G;
   const int *act;        // [J]
-  const int *ref_group;  // [J] group (frame) of the instance's reference voxels
+  const int *ref_group;  // [J] group of the instance's reference voxels (non-stationary voxels of its key and frame)
+  const int *ref_group_all;  // [J] group holding ALL voxels of the target frame (matched-fraction search)
   const int *skipmask;   // [J] stationary bit of the instance's component key
   const int *ref_off;    // [n_groups + 1] voxel range of every group in the (group-major) reference array
   const int *g_inst;     // [G]
@@ -556,16 +691,20 @@ struct IcpB {
   const int *mv_inst;
   const int *n_mv;  // device count
   const int *vdeg;  // [G] voxels per component (stationary ones included)
-  float r2, acc0;
+  float r2, acc0, cover2;
+  int batch;
+  int rings, mode;  // mode 0: warp search seeded with the previous neighbour, 1: + thread-level fast path, 2: unseeded
   double angle_reg, stopping_delta;
   int max_iter, want_l1, want_ratio;
   int *nn_fwd, *nn_bwd, *boff;
+  int *mvbeg, *mvend;  // [J] rows of every instance in the moving voxel array (voxels are grouped by instance)
   double *mom, *Ti, *T, *mu, *l1_sum, *l1_n;
   int *phase, *cd, *iters, *itcnt;
   double *last, *loss;
   int *match_cnt;
   double *l1_err;
   float *ratio;
+  long long *prof;  // optional [16]: nanoseconds per phase (B, C, D, E, F, G, H, tail), [8] iterations, [9] launches
 };
 
 // same solve as icp.cu (kept there for the single-instance entry point)
@@ -639,6 +778,7 @@ __global__ void __launch_bounds__(256) trk_icp_setup_kernel(IcpB A) {
     if (A.want_l1) A.l1_err[i] = 0.0;
   }
   if (i < A.J) {
+    A.mvbeg[i] = A.mvend[i] = 0;
     A.phase[i] = A.act[i] ? PH_RUN : PH_FROZEN;
     A.cd[i] = 3;
     A.iters[i] = 0;
@@ -657,6 +797,15 @@ __global__ void __launch_bounds__(256) trk_icp_setup_kernel(IcpB A) {
   }
 }
 
+__global__ void __launch_bounds__(256) trk_icp_ranges_kernel(IcpB A) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = *A.n_mv;
+  if (v >= n) return;
+  const int inst = A.mv_inst[v];
+  if (v == 0 || A.mv_inst[v - 1] != inst) A.mvbeg[inst] = v;
+  if (v == n - 1 || A.mv_inst[v + 1] != inst) A.mvend[inst] = v + 1;
+}
+
 // edge of work item w: forward items are the moving voxels, backward items the instances' reference voxels
 __device__ __forceinline__ bool icp_edge_of(const IcpB &A, int w, int nmv, int &mi, int &ri, int want_phase) {
   if (w < nmv) {
@@ -673,8 +822,26 @@ __device__ __forceinline__ bool icp_edge_of(const IcpB &A, int w, int nmv, int &
   return mi >= 0 && ri >= 0;
 }
 
-__global__ void __launch_bounds__(kTrkThreads, 2) trk_icp_kernel(IcpB A) {
+__device__ __forceinline__ long long gtime() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+#define ICP_PROF(slot)                                   \
+  if (A.prof && tid == 0) {                              \
+    const long long now_ = gtime();                      \
+    A.prof[slot] += now_ - t_prev;                       \
+    t_prev = now_;                                       \
+  }
+
+constexpr int kMaxInst = 1024;
+
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kTrkThreads, kMinBlocks) trk_icp_kernel(IcpB A) {
+  __shared__ int s_aoff[kMaxInst + 1];
   cg::grid_group grid = cg::this_grid();
+  long long t_prev = gtime();
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long nth = (long long)gridDim.x * blockDim.x;
   const int lane = threadIdx.x & 31;
@@ -697,9 +864,11 @@ __global__ void __launch_bounds__(kTrkThreads, 2) trk_icp_kernel(IcpB A) {
       pg_count(A.mov, j, p.y, p.z, p.w);
     }
     grid.sync();
+    ICP_PROF(0)
     // ---- C: ranges -----------------------------------------------------------------------------------------
     pg_ranges(A.mov, tid, nth);
     grid.sync();
+    ICP_PROF(1)
     // ---- D: scatter ----------------------------------------------------------------------------------------
     for (long long v = tid; v < nmv; v += nth) {
       const int j = A.mv_inst[v];
@@ -708,58 +877,145 @@ __global__ void __launch_bounds__(kTrkThreads, 2) trk_icp_kernel(IcpB A) {
       pg_scatter(A.mov, j, p.y, p.z, p.w, 0u, (int)v);
     }
     grid.sync();
+    ICP_PROF(2)
     // ---- E: both nearest-neighbour searches + raw moments of the edge set -------------------------------------
-    const long long nchunks = ((long long)total + CH - 1) / CH;
-    for (long long ch = warp_id; ch < nchunks; ch += nwarps) {
-      int cur = -1;
-      double acc = 0.0;
-      const int w1 = (int)min((long long)total, (ch + 1) * CH);
-      for (int w = (int)(ch * CH); w < w1; w++) {
-        int mi, ri;
-        float4 mp, rp;
-        if (w < nmv) {  // forward: moving voxel -> nearest non-stationary reference voxel
-          mi = w;
-          const int j = A.mv_inst[mi];
-          if (A.phase[j] != PH_RUN) continue;
-          mp = A.mv[mi];
-          ri = nn_search(A.ref, false, A.ref_group[j], mp.y, mp.z, mp.w, A.acc0, A.r2, (unsigned int)A.skipmask[j], lane);
-          if (A.want_l1 && lane == 0) A.nn_fwd[mi] = ri;
-          if (ri < 0) continue;
-          rp = A.ref.sorted[ri];
-        } else {  // backward: non-stationary reference voxel -> nearest moving voxel of the instance
-          const int b = w - nmv;
-          const int j = seg_of_item(A.boff, A.J, b);
-          if (A.phase[j] != PH_RUN) continue;
-          ri = A.ref_off[A.ref_group[j]] + (b - A.boff[j]);
-          rp = A.ref.sorted[ri];
-          mi = -1;
-          if (!(__float_as_uint(rp.x) & (unsigned int)A.skipmask[j]))
-            mi = nn_search(A.mov, true, j, rp.y, rp.z, rp.w, A.acc0, A.r2, 0u, lane);
-          if (A.want_l1 && lane == 0) A.nn_bwd[b] = mi;
-          if (mi < 0) continue;
-          mp = A.mv[mi];
-        }
-        const int c = A.mv_gid[mi];
-        if (c != cur) {
-          if (cur >= 0 && lane < kMomN) atomicAdd(A.mom + (long long)cur * kMomN + lane, acc);
-          cur = c;
-          acc = 0.0;
-        }
-        const double m[3] = {mp.y, mp.z, mp.w}, r[3] = {rp.y, rp.z, rp.w};
-        double v = 0.0;
-        if (lane == 0) v = 1.0;
-        else if (lane < 4) v = m[lane - 1];
-        else if (lane < 7) v = r[lane - 4];
-        else if (lane < 16) v = m[(lane - 7) / 3] * r[(lane - 7) % 3];
-        else if (lane == 16) {
-          const double dx = m[0] - r[0], dy = m[1] - r[1], dz = m[2] - r[2];
-          v = dx * dx + dy * dy + dz * dz;
-        }
-        acc += v;
+    // One work item per lane.  A query whose neighbour of the previous iteration is still within one cell is
+    // settled by its own thread (27 fine cells, bound = that distance: exact); the others -- first iteration, lost
+    // or far neighbours -- are searched by the whole warp, one after the other, over the 5x5x5 block.
+    // active work items of this iteration: [forward voxels | backward reference voxels] of every running instance
+    if (threadIdx.x == 0) {
+      int o = 0;
+      for (int jj = 0; jj < A.J; jj++) {
+        s_aoff[jj] = o;
+        if (A.phase[jj] == PH_RUN) o += (A.mvend[jj] - A.mvbeg[jj]) + (A.boff[jj + 1] - A.boff[jj]);
       }
-      if (cur >= 0 && lane < kMomN) atomicAdd(A.mom + (long long)cur * kMomN + lane, acc);
+      s_aoff[A.J] = o;
+    }
+    __syncthreads();
+    const int n_active = s_aoff[A.J];
+    const int BQ = A.batch;  // work items per warp batch (<= 32)
+    const long long nbatch = ((long long)n_active + BQ - 1) / BQ;
+    // consecutive batches go to different CTAs (SMs): the costly regions of the item axis are spread over the chip
+    for (long long batch = (long long)(threadIdx.x >> 5) * gridDim.x + blockIdx.x; batch < nbatch; batch += nwarps) {
+      const int w = (int)(batch * BQ) + lane;
+      bool active = lane < BQ && w < n_active;
+      bool fwd = true;
+      int mi = -1, ri = -1, j = 0, prev = -1, b = 0;
+      float qx = 0.f, qy = 0.f, qz = 0.f;
+      unsigned int skip = 0u;
+      if (active) {
+        j = seg_of_item(s_aoff, A.J, w);
+        const int local = w - s_aoff[j];
+        const int nf = A.mvend[j] - A.mvbeg[j];
+        fwd = local < nf;
+        if (fwd) {  // forward: moving voxel -> nearest non-stationary reference voxel
+          mi = A.mvbeg[j] + local;
+          const float4 q = A.mv[mi];
+          qx = q.y, qy = q.z, qz = q.w;
+          skip = (unsigned int)A.skipmask[j];
+          prev = it > 0 ? A.nn_fwd[mi] : -1;
+        } else {  // backward: non-stationary reference voxel -> nearest moving voxel of the instance
+          b = A.boff[j] + (local - nf);
+          ri = A.ref_off[A.ref_group[j]] + (local - nf);
+          const float4 q = A.ref.sorted[ri];
+          qx = q.y, qy = q.z, qz = q.w;
+          if (__float_as_uint(q.x) & (unsigned int)A.skipmask[j]) {
+            active = false;
+            A.nn_bwd[b] = -1;
+          } else {
+            prev = it > 0 ? A.nn_bwd[b] : -1;
+          }
+        }
+      }
+      int res = -1;
+      bool need_warp = active;
+      unsigned long long pkey0 = ~0ull;  // the previous neighbour as a first candidate
+      if (active && prev >= 0) {
+        const float4 c = fwd ? A.ref.sorted[prev] : A.mv[prev];
+        const float d2p = dist2_acc(A.acc0, c.y, c.z, c.w, qx, qy, qz);
+        if (d2p <= A.r2) pkey0 = ((unsigned long long)__float_as_uint(d2p) << 32) | (unsigned int)prev;
+        if (A.mode == 1 && d2p <= A.r2 && d2p - A.acc0 <= A.cover2) {
+          const unsigned long long k = fwd ? nn_search_thread(A.ref, false, A.ref_group[j], qx, qy, qz, A.acc0, d2p, skip)
+                                           : nn_search_thread(A.mov, true, j, qx, qy, qz, A.acc0, d2p, 0u);
+          res = k == ~0ull ? prev : (int)(unsigned int)(k & 0xffffffffu);
+          need_warp = false;
+        }
+      }
+      unsigned int todo = __ballot_sync(kAll, need_warp);
+      if (A.prof) {
+        const unsigned int na = __ballot_sync(kAll, active);
+        if (lane == 0 && na) {
+          atomicAdd((unsigned long long *)A.prof + 10, (unsigned long long)__popc(na & ~todo));
+          atomicAdd((unsigned long long *)A.prof + 11, (unsigned long long)__popc(todo));
+          if (it < 96) atomicAdd((unsigned long long *)A.prof + 112 + it, (unsigned long long)__popc(na));
+        }
+      }
+      while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const bool sf = __shfl_sync(kAll, (int)fwd, src) != 0;
+        const int sj = __shfl_sync(kAll, j, src);
+        const float sx = __shfl_sync(kAll, qx, src), sy = __shfl_sync(kAll, qy, src), sz = __shfl_sync(kAll, qz, src);
+        const unsigned int ss = __shfl_sync(kAll, skip, src);
+        const unsigned long long sk = A.mode == 2 ? ~0ull : __shfl_sync(kAll, pkey0, src);
+        const int r = sf ? nn_search_rings(A.ref, false, A.ref_group[sj], sx, sy, sz, A.acc0, A.r2, ss, lane, A.rings, sk)
+                         : nn_search_rings(A.mov, true, sj, sx, sy, sz, A.acc0, A.r2, 0u, lane, A.rings, sk);
+        if (lane == src) res = r;
+      }
+      int c = -1;
+      float4 mp = make_float4(0.f, 0.f, 0.f, 0.f), rp = mp;
+      if (active) {
+        if (fwd) {
+          A.nn_fwd[mi] = res;
+          ri = res;
+        } else {
+          A.nn_bwd[b] = res;
+          mi = res;
+        }
+        if (res >= 0) {
+          mp = A.mv[mi];
+          rp = A.ref.sorted[ri];
+          c = A.mv_gid[mi];
+        }
+      }
+      if (A.prof) {
+        const unsigned int nu = __ballot_sync(kAll, active && res < 0);
+        if (lane == 0 && nu) atomicAdd((unsigned long long *)A.prof + 12, (unsigned long long)__popc(nu));
+      }
+      // raw moments: segmented warp sums over runs of equal component, one set of atomics per run
+      {
+        const int prevc = __shfl_up_sync(kAll, c, 1);
+        const bool head = lane == 0 || prevc != c;
+        const unsigned int heads = __ballot_sync(kAll, head);
+        if (__ballot_sync(kAll, c >= 0) != 0u) {
+          const unsigned int above = lane == 31 ? 0u : (heads & (0xfffffffeu << lane));
+          const int end = above ? (__ffs(above) - 1) : 32;
+          const double m[3] = {mp.y, mp.z, mp.w}, r[3] = {rp.y, rp.z, rp.w};
+#pragma unroll
+          for (int k = 0; k < kMomN; k++) {
+            double v;
+            if (k == 0) v = 1.0;
+            else if (k < 4) v = m[k - 1];
+            else if (k < 7) v = r[k - 4];
+            else if (k < 16) v = m[(k - 7) / 3] * r[(k - 7) % 3];
+            else {
+              const double dx = m[0] - r[0], dy = m[1] - r[1], dz = m[2] - r[2];
+              v = dx * dx + dy * dy + dz * dz;
+            }
+            if (c < 0) v = 0.0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+              const double tv = __shfl_down_sync(kAll, v, o);
+              if (lane + o < end) v += tv;
+            }
+            if (head && c >= 0) atomicAdd(A.mom + (long long)c * kMomN + k, v);
+          }
+        }
+      }
     }
     grid.sync();
+    if (A.prof && tid == 0 && it < 96) A.prof[16 + it] += gtime() - t_prev;
+    ICP_PROF(3)
     // ---- F: per-component solve (thread per component) + instance loss ; the moving grid is released ----------
     for (long long c0 = tid - lane; c0 < A.G; c0 += nth) {
       const long long c = c0 + lane;
@@ -826,6 +1082,7 @@ __global__ void __launch_bounds__(kTrkThreads, 2) trk_icp_kernel(IcpB A) {
     }
     pg_clear_used(A.mov, tid, nth);
     grid.sync();
+    ICP_PROF(4)
     // ---- G: stopping rule per instance (:180-186) ---------------------------------------------------------------
     if (tid < A.J) {
       const int j = (int)tid;
@@ -850,6 +1107,8 @@ __global__ void __launch_bounds__(kTrkThreads, 2) trk_icp_kernel(IcpB A) {
     }
     if (tid == 0) A.mov.ctr[0] = A.mov.ctr[1] = 0;
     grid.sync();
+    ICP_PROF(5)
+    if (A.prof && tid == 0) A.prof[8] += 1;
     const int n_fin = A.itcnt[it * 2 + 0], n_run = A.itcnt[it * 2 + 1];
     if (n_fin > 0) {
       if (A.want_l1) {
@@ -887,37 +1146,50 @@ __global__ void __launch_bounds__(kTrkThreads, 2) trk_icp_kernel(IcpB A) {
         apply_T(p, A.Ti + (long long)A.mv_gid[v] * 12);
         A.mv[v] = p;
       }
+      ICP_PROF(6)
     }
     if (n_run == 0) break;
   }
+  if (A.prof && tid == 0) A.prof[9] += 1;
   if (A.want_ratio) {
     grid.sync();
-    // matched fraction: moving voxels with ANY reference voxel (stationary included) within the radius (:189-199)
-    const long long nchunks = ((long long)nmv + CH - 1) / CH;
-    for (long long ch = warp_id; ch < nchunks; ch += nwarps) {
-      int cur = -1, cnt = 0;
-      const int w1 = (int)min((long long)nmv, (ch + 1) * CH);
-      for (int w = (int)(ch * CH); w < w1; w++) {
-        const int j = A.mv_inst[w];
-        if (!A.act[j]) continue;
-        const float4 mp = A.mv[w];
-        const int ri = nn_search(A.ref, false, A.ref_group[j], mp.y, mp.z, mp.w, A.acc0, A.r2, 0u, lane);
-        if (ri < 0) continue;
-        const int c = A.mv_gid[w];
-        if (c != cur) {
-          if (cur >= 0 && lane == 0) atomicAdd(A.match_cnt + cur, cnt);
-          cur = c;
-          cnt = 0;
-        }
-        cnt++;
+    // matched fraction: moving voxels with ANY reference voxel (stationary included) within the radius (:189-199).
+    // The neighbour of the last iteration usually still is within the radius at the final position: no search then.
+    for (long long base = warp_id * 32; base < nmv; base += nwarps * 32) {
+      const int w = (int)base + lane;
+      bool active = w < nmv;
+      int j = 0;
+      float4 mp = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (active) {
+        j = A.mv_inst[w];
+        active = A.act[j] != 0;
+        if (active) mp = A.mv[w];
       }
-      if (cur >= 0 && lane == 0) atomicAdd(A.match_cnt + cur, cnt);
+      bool matched = false;
+      if (active) {
+        const int prev = A.nn_fwd[w];
+        if (prev >= 0) {
+          const float4 c = A.ref.sorted[prev];
+          matched = dist2_acc(A.acc0, c.y, c.z, c.w, mp.y, mp.z, mp.w) <= A.r2;
+        }
+      }
+      unsigned int todo = __ballot_sync(kAll, active && !matched);
+      while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int sj = __shfl_sync(kAll, j, src);
+        const float sx = __shfl_sync(kAll, mp.y, src), sy = __shfl_sync(kAll, mp.z, src), sz = __shfl_sync(kAll, mp.w, src);
+        const int r = nn_search_rings(A.ref, false, A.ref_group_all[sj], sx, sy, sz, A.acc0, A.r2, 0u, lane, A.rings);
+        if (lane == src) matched = r >= 0;
+      }
+      if (matched) atomicAdd(A.match_cnt + A.mv_gid[w], 1);
     }
     grid.sync();
     for (long long c = tid; c < A.G; c += nth) {
       if (!A.act[A.g_inst[c]]) continue;
       A.ratio[c] = (float)A.match_cnt[c] / ((float)A.vdeg[c] + 1e-6f);  // :199
     }
+    ICP_PROF(7)
   }
 }
 
@@ -950,7 +1222,8 @@ struct Trk {
   double *T;  // [G][12] level transform (written by the ICP kernel)
   int *vdeg;  // [G] voxels per component of the level-0 sampling (consumed by the level-0 ICP)
   // per-step instance state
-  int *cur_act, *cur_nxt, *cur_rel, *cur_haslv, *anyns /*[18][J]*/;
+  int *cur_act, *cur_nxt, *cur_rel, *cur_haslv, *cur_grp, *cur_grp_all, *anyns /*[18][J]*/;
+  int n_keys;
   unsigned int *sb;  // [J][6] bounds for the sampler
   // parameters
   float reg_error_coeff, angle_threshold;
@@ -981,6 +1254,9 @@ __global__ void __launch_bounds__(128) trk_step_begin_kernel(Trk A, int t) {
   else act = A.cur_act[j] && A.anyns[(t - 1) * A.J + j] && inr;
   A.cur_act[j] = act;
   A.cur_nxt[j] = nxt;
+  const int fcl = nxt < 0 ? 0 : (nxt >= A.F ? A.F - 1 : nxt);
+  A.cur_grp[j] = A.inst_key[j] * A.F + fcl;
+  A.cur_grp_all[j] = A.n_keys * A.F + fcl;
   A.cur_rel[j] = kAnchorRel + dir * s;
   A.cur_haslv[j] = dir < 0 ? (s >= 2) : (s >= 2 || a > 0);
   if (j == 0) {
@@ -1469,6 +1745,7 @@ IcpB make_icp(const pcs_trk_icp_t *P) {
   A.G = (int)P->G;
   A.act = (const int *)P->act;
   A.ref_group = (const int *)P->ref_group;
+  A.ref_group_all = (const int *)P->ref_group_all;
   A.skipmask = (const int *)P->skipmask;
   A.ref_off = (const int *)P->ref_off;
   A.g_inst = (const int *)P->g_inst;
@@ -1482,6 +1759,18 @@ IcpB make_icp(const pcs_trk_icp_t *P) {
   const float r = (float)P->radius;
   A.r2 = r * r;
   A.acc0 = (float)((double)P->df * (double)P->df);
+  A.rings = (int)P->rings < 2 ? 1 : 2;
+  {
+    const char *m = getenv("PCS_ICP_MODE");
+    A.mode = m ? atoi(m) : 0;
+    const char *bq = getenv("PCS_ICP_BATCH");
+    A.batch = bq ? atoi(bq) : 8;
+    if (A.batch < 1 || A.batch > 32) A.batch = 32;
+  }
+  {
+    const float cover = 0.98f * (float)P->cs;
+    A.cover2 = cover * cover;
+  }
   A.angle_reg = P->angle_reg;
   A.stopping_delta = P->stopping_delta;
   A.max_iter = (int)P->max_iter;
@@ -1490,6 +1779,8 @@ IcpB make_icp(const pcs_trk_icp_t *P) {
   A.nn_fwd = (int *)P->nn_fwd;
   A.nn_bwd = (int *)P->nn_bwd;
   A.boff = (int *)P->boff;
+  A.mvbeg = (int *)P->mvbeg;
+  A.mvend = (int *)P->mvend;
   A.mom = (double *)P->mom;
   A.Ti = (double *)P->Ti;
   A.T = (double *)P->T;
@@ -1505,6 +1796,7 @@ IcpB make_icp(const pcs_trk_icp_t *P) {
   A.match_cnt = (int *)P->match_cnt;
   A.l1_err = (double *)P->l1_err;
   A.ratio = (float *)P->ratio;
+  A.prof = (long long *)P->prof;
   return A;
 }
 
@@ -1556,6 +1848,9 @@ Trk make_trk(const pcs_trk_ctx_t *C) {
   A.cur_nxt = (int *)C->cur_nxt;
   A.cur_rel = (int *)C->cur_rel;
   A.cur_haslv = (int *)C->cur_haslv;
+  A.cur_grp = (int *)C->cur_grp;
+  A.cur_grp_all = (int *)C->cur_grp_all;
+  A.n_keys = (int)C->n_keys;
   A.anyns = (int *)C->anyns;
   A.sb = (unsigned int *)C->sb;
   A.reg_error_coeff = (float)C->reg_error_coeff;
@@ -1573,13 +1868,13 @@ Trk make_trk(const pcs_trk_ctx_t *C) {
 
 inline unsigned int blocks_for(long long n, int block) { return (unsigned int)((n > 0 ? n : 1) + block - 1) / block; }
 
-int coop_grid(const void *kernel, int threads, long long want_threads) {
+int coop_grid(const void *kernel, int threads, long long want_threads, int max_per_sm = 2) {
   int dev = 0, sms = 148, per_sm = 1;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0);
   if (per_sm < 1) per_sm = 1;
-  if (per_sm > 2) per_sm = 2;
+  if (per_sm > max_per_sm) per_sm = max_per_sm;
   long long blocks = (want_threads + threads - 1) / threads;
   const long long cap = (long long)sms * per_sm;
   if (blocks > cap) blocks = cap;
@@ -1669,10 +1964,18 @@ static int launch_icp(cudaStream_t st, const pcs_trk_icp_t *P) {
   IcpB A = make_icp(P);
   long long cover = P->G > P->J ? P->G : P->J;
   if ((P->max_iter + 2) * 2 > cover) cover = (P->max_iter + 2) * 2;
+  if (P->J > kMaxInst) return set_error(PCS_ERR_BAD_ARG, "pcs_trk_icp: more than 1024 instances");
   PCS_LAUNCH(trk_icp_setup_kernel, blocks_for(cover, 256), 256, 0, st, A);
-  const int blocks = coop_grid((const void *)trk_icp_kernel, kTrkThreads, 1LL << 40);
+  PCS_LAUNCH(trk_icp_ranges_kernel, blocks_for(P->mv_cap > 0 ? P->mv_cap : 1, 256), 256, 0, st, A);
+  static int occ = -1;
+  if (occ < 0) {
+    const char *o = getenv("PCS_ICP_OCC");
+    occ = o ? atoi(o) : 4;
+  }
+  const void *kern = occ >= 4 ? (const void *)trk_icp_kernel<4> : (occ == 3 ? (const void *)trk_icp_kernel<3> : (const void *)trk_icp_kernel<2>);
+  const int blocks = coop_grid(kern, kTrkThreads, 1LL << 40, occ >= 4 ? 4 : (occ == 3 ? 3 : 2));
   void *args[] = {&A};
-  cudaError_t e = cudaLaunchCooperativeKernel((void *)trk_icp_kernel, dim3((unsigned)blocks), dim3(kTrkThreads), args, 0, st);
+  cudaError_t e = cudaLaunchCooperativeKernel(kern, dim3((unsigned)blocks), dim3(kTrkThreads), args, 0, st);
   g_launches++;
   if (e != cudaSuccess) return set_error((int)e, "trk_icp_kernel (cooperative launch)");
   return check_launch("trk_icp_kernel");

@@ -536,11 +536,26 @@ class ClusterTracking(nn.Module):
         results = {}
         if self.batched:
             from ..tracker import TrackBatch
+            import time as _time
+            timing = os.environ.get("PCS_TRACK_TIMING")
+            marks = []
+
+            def mark(name):
+                if timing:
+                    torch.cuda.synchronize()
+                    marks.append((name, _time.perf_counter()))
+
+            mark("start")
             comps = [seq_dict[f"point_{k}"] for k in self.component_keys]
-            tb = TrackBatch(seq_points.fxyz, seq_points.frame, comps, self.model_cfg, num_frames=num_frames).run()
+            tb = TrackBatch(seq_points.fxyz, seq_points.frame, comps, self.model_cfg, num_frames=num_frames)
+            mark("setup")
+            tb.run()
+            mark("run")
             per_inst = tb.results(seg_label=seq_points.get("segmentation_label"))
             tb.check()
+            mark("results")
             full = self.extract_traces_batched(tb, all_points, seq_boxes)
+            mark("extract_traces")
             lazy = self.model_cfg.get("LAZY_TRANSFORMS", False) and not save
             for ki, comp_key in enumerate(self.component_keys):
                 for frame_id in tb.anchors:
@@ -553,6 +568,21 @@ class ClusterTracking(nn.Module):
                         torch.save(extracted, f"{outfolder}/{frame_id:03d}_{comp_key}.pth")
                     results[f"{frame_id:03d}_{comp_key}"] = extracted
             seq_dict["tracking_batch"] = tb
+            mark("assemble")
+            if timing:
+                names = ["count", "ranges", "scatter", "search", "solve", "stop", "final", "ratio"]
+                for lv, pr in enumerate(tb.prof):
+                    pr = pr.tolist()
+                    print(f"[icp level {lv}] launches {pr[9]} iterations {pr[8]} thread-path {pr[10]} warp-path {pr[11]} "
+                          f"unmatched {pr[12]} " +
+                          ", ".join(f"{n} {pr[i] / 1e6:.1f} ms" for i, n in enumerate(names)), flush=True)
+                    if os.environ.get("PCS_TRACK_TIMING") == "2":
+                        print("   per-iteration search ms (summed over launches): " +
+                              " ".join(f"{pr[16 + i] / 1e6:.1f}" for i in range(80)))
+                        print("   per-iteration active queries (k): " +
+                              " ".join(f"{pr[112 + i] // 1000}" for i in range(80)))
+                print("[track timing] " + ", ".join(f"{n} {1e3 * (t - marks[i][1]):.1f} ms"
+                                                    for i, (n, t) in enumerate(marks[1:])), flush=True)
         else:
             for comp_key in self.component_keys:
                 seq_points.component = seq_dict[f"point_{comp_key}"]

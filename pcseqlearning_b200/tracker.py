@@ -20,6 +20,8 @@ from .utils import EasyDict
 STATIONARY_DIAMETER = 12.5  # cluster_tracking.py:861 / filter_components default
 REL = 17                    # relative frame window [anchor - 8, anchor + 8]
 ANCHOR_REL = 8
+ICP_RINGS = int(__import__('os').environ.get('PCS_ICP_RINGS', '1'))  # 1: cell = radius, 3x3x3 search (measured
+# faster than 2: cells of half the radius searched over 5x5x5 -- the shell lookups of unmatched queries dominate)
 
 
 def _mk_struct(name, fields):
@@ -37,16 +39,17 @@ SamplerStruct = _mk_struct("pcs_trk_sampler_t", [
     ("out_pts", _P), ("out_key", _P), ("out_group", _P)])
 
 IcpStruct = _mk_struct("pcs_trk_icp_t", [
-    ("J", _I), ("G", _I), ("act", _P), ("ref_group", _P), ("skipmask", _P), ("ref_off", _P), ("g_inst", _P),
+    ("J", _I), ("G", _I), ("act", _P), ("ref_group", _P), ("ref_group_all", _P), ("skipmask", _P), ("ref_off", _P),
+    ("g_inst", _P),
     ("ref_table", _P), ("ref_H", _I), ("ref_pts", _P),
     ("mov_table", _P), ("mov_H", _I), ("mov_sorted", _P), ("mov_sidx", _P), ("mov_cells", _P), ("mov_ctr", _P),
-    ("mv", _P), ("mv_gid", _P), ("mv_inst", _P), ("n_mv", _P), ("vdeg", _P),
-    ("lo", _D * 3), ("cs", _D), ("radius", _D), ("df", _I), ("angle_reg", _D), ("max_iter", _I),
+    ("mv", _P), ("mv_gid", _P), ("mv_inst", _P), ("n_mv", _P), ("mv_cap", _I), ("vdeg", _P),
+    ("lo", _D * 3), ("cs", _D), ("rings", _I), ("radius", _D), ("df", _I), ("angle_reg", _D), ("max_iter", _I),
     ("stopping_delta", _D), ("want_l1", _I), ("want_ratio", _I),
-    ("nn_fwd", _P), ("nn_bwd", _P), ("boff", _P),
+    ("nn_fwd", _P), ("nn_bwd", _P), ("boff", _P), ("mvbeg", _P), ("mvend", _P),
     ("mom", _P), ("Ti", _P), ("T", _P), ("mu", _P), ("l1_sum", _P), ("l1_n", _P),
     ("phase", _P), ("cd", _P), ("iters", _P), ("itcnt", _P), ("last", _P), ("loss", _P), ("match_cnt", _P),
-    ("l1_err", _P), ("ratio", _P)])
+    ("l1_err", _P), ("ratio", _P), ("prof", _P)])
 
 CtxStruct = _mk_struct("pcs_trk_ctx_t", [
     ("J", _I), ("G", _I), ("M", _I), ("F", _I),
@@ -59,7 +62,8 @@ CtxStruct = _mk_struct("pcs_trk_ctx_t", [
     ("transforms", _P), ("velos", _P), ("velos_b", _P), ("centers", _P), ("diffs", _P),
     ("cv_pre", _P), ("g_delta", _P), ("adam_m", _P), ("adam_v", _P),
     ("csum", _P), ("vsum", _P), ("l1_err", _P), ("ratio", _P), ("T", _P), ("vdeg", _P),
-    ("cur_act", _P), ("cur_nxt", _P), ("cur_rel", _P), ("cur_haslv", _P), ("anyns", _P), ("sb", _P),
+    ("cur_act", _P), ("cur_nxt", _P), ("cur_rel", _P), ("cur_haslv", _P), ("cur_grp", _P), ("cur_grp_all", _P),
+    ("n_keys", _I), ("anyns", _P), ("sb", _P),
     ("reg_error_coeff", _D), ("angle_threshold", _D), ("min_move_frame", _I),
     ("radius", _D * 8), ("voxel_size", _D * 24), ("lo", _D * 3), ("nn_radius", _D),
     ("eg_table", _P), ("eg_H", _I), ("eg_sorted", _P), ("eg_sidx", _P), ("eg_cells", _P), ("eg_ctr", _P),
@@ -283,14 +287,29 @@ class TrackBatch:
                                          self.voxel_size[lv], sb_f, None, out_pts, out_key, out_group)
                 _lib.check(L.pcs_trk_sample(s, ctypes.byref(st)), "pcs_trk_sample (static)")
                 V = int(self.sampler.t["ctr"][1].item())
-                cs = self.radius[lv] * 1.001
+                cs = self.radius[lv] * 1.001 / ICP_RINGS
                 lo_c = (ctypes.c_double * 3)(*lo)
-                keys = _e(V, torch.int64, dev)
-                _lib.check(L.pcs_trk_cell_keys(s, _ptr(out_pts), _ptr(out_group), V, lo_c, cs, _ptr(keys)),
-                           "pcs_trk_cell_keys")
+                # One grid per level holds, for every component key k, the NON-stationary voxels of every frame
+                # (group = k * F + frame: the ICP never has to step over the stationary bulk -- buildings, walls --
+                # of a cell) and, as pseudo-key nK, all voxels (group = nK * F + frame: the matched-fraction search).
+                vp, vf = out_pts[:V], out_group[:V].long()
+                bits = vp[:, 0].contiguous().view(torch.int32)
+                sel_pts, sel_grp = [], []
+                for ki in range(nK):
+                    ns = ((bits >> ki) & 1) == 0
+                    sel_pts.append(vp[ns])
+                    sel_grp.append(vf[ns] + ki * F)
+                sel_pts.append(vp)
+                sel_grp.append(vf + nK * F)
+                cat_pts = torch.cat(sel_pts).contiguous()
+                cat_grp = torch.cat(sel_grp)
+                Vc = int(cat_pts.shape[0])
+                keys = _e(Vc, torch.int64, dev)
+                _lib.check(L.pcs_trk_cell_keys(s, _ptr(cat_pts), _ptr(cat_grp.int().contiguous()), Vc, lo_c, cs,
+                                               _ptr(keys)), "pcs_trk_cell_keys")
                 ks, perm = torch.sort(keys)
-                rv = out_pts[:V][perm].contiguous()
-                rv_frame = out_group[:V][perm].long()
+                rv = cat_pts[perm].contiguous()
+                rv_grp = cat_grp[perm]
                 uk, cnt = torch.unique_consecutive(ks, return_counts=True)
                 starts = (cnt.cumsum(0) - cnt).int().contiguous()
                 ncell = int(uk.shape[0])
@@ -299,10 +318,11 @@ class TrackBatch:
                 err = _z(1, torch.int32, dev)
                 _lib.check(L.pcs_trk_grid_fill(s, _ptr(table), Hc, _ptr(uk), _ptr(starts), _ptr(cnt.int().contiguous()),
                                                ncell, _ptr(err)), "pcs_trk_grid_fill")
-                rv_off = torch.zeros(F + 1, dtype=torch.int64, device=dev)
-                rv_off[1:] = torch.bincount(rv_frame, minlength=F).cumsum(0)
+                n_grp = (nK + 1) * F
+                rv_off = torch.zeros(n_grp + 1, dtype=torch.int64, device=dev)
+                rv_off[1:] = torch.bincount(rv_grp, minlength=n_grp).cumsum(0)
                 rv_off_h = rv_off.tolist()
-                max_cnt = max(rv_off_h[f + 1] - rv_off_h[f] for f in range(F))
+                max_cnt = max(rv_off_h[g + 1] - rv_off_h[g] for g in range(nK * F))
                 self.levels.append(dict(rv=rv, rv_off=rv_off.int().contiguous(), table=table, H=Hc, cs=cs, V=V,
                                         bwd_cap=max(J * max_cnt, 1), err=err))
 
@@ -329,7 +349,7 @@ class TrackBatch:
             t["csum"], t["vsum"] = _z((G, 3), torch.float64, dev), _z((G, 3), torch.float64, dev)
             t["l1_err"], t["ratio"] = _z(G, torch.float64, dev), _z(G, torch.float32, dev)
             t["T"], t["vdeg"] = _z((G, 12), torch.float64, dev), _z(G, torch.int32, dev)
-            for k in ("cur_act", "cur_nxt", "cur_rel", "cur_haslv"):
+            for k in ("cur_act", "cur_nxt", "cur_rel", "cur_haslv", "cur_grp", "cur_grp_all"):
                 t[k] = _z(J, torch.int32, dev)
             t["anyns"] = _z((REL + 1, J), torch.int32, dev)
             t["sb"] = _e((J, 6), torch.int32, dev)
@@ -363,7 +383,7 @@ class TrackBatch:
             self.t = t
 
             ctx = CtxStruct()
-            _fill(ctx, self.keep, J=J, G=G, M=M, F=F, reg_error_coeff=float(params.get("REGISTRATION_ERROR_COEFFICIENT", 0.13)),
+            _fill(ctx, self.keep, J=J, G=G, M=M, F=F, n_keys=nK, reg_error_coeff=float(params.get("REGISTRATION_ERROR_COEFFICIENT", 0.13)),
                   angle_threshold=float(params.get("ANGLE_THRESHOLD", 45)), min_move_frame=self.min_move,
                   nn_radius=self.nn_radius, eg_H=He, lo=lo, **t)
             for lv in range(self.n_levels):
@@ -382,6 +402,7 @@ class TrackBatch:
             sc = dict(mov_table=_e((Hm, 4), torch.int32, dev), mov_sorted=_e((M, 4), torch.float32, dev),
                       mov_sidx=_e(M, torch.int32, dev), mov_cells=_e(M, torch.int32, dev), mov_ctr=_z(4, torch.int32, dev),
                       nn_fwd=_e(M, torch.int32, dev), boff=_z(J + 1, torch.int32, dev),
+                      mvbeg=_z(J, torch.int32, dev), mvend=_z(J, torch.int32, dev),
                       mom=_z((G, 17), torch.float64, dev), Ti=_z((G, 12), torch.float64, dev), mu=_z((G, 6), torch.float64, dev),
                       l1_sum=_z((G, 2), torch.float64, dev), l1_n=_z(G, torch.float64, dev),
                       phase=_z(J, torch.int32, dev), cd=_z(J, torch.int32, dev), iters=_z(J, torch.int32, dev),
@@ -390,17 +411,19 @@ class TrackBatch:
             _lib.check(L.pcs_trk_table_clear(s, _ptr(sc["mov_table"]), Hm, _ptr(sc["mov_ctr"])), "pcs_trk_table_clear")
             self.sc = sc
             nn_bwd = _e(max(lv["bwd_cap"] for lv in self.levels), torch.int32, dev)
-            self.skipmask = (1 << inst_key).int().contiguous()
-            self.iters_log = []
+            self.skipmask = torch.zeros(J, dtype=torch.int32, device=dev)  # the grids hold non-stationary voxels only
+            self.prof = [_z(256, torch.int64, dev) for _ in range(self.n_levels)]
             icp_arr = (IcpStruct * self.n_levels)()
             for lv in range(self.n_levels):
                 d = self.levels[lv]
-                _fill(icp_arr[lv], self.keep, J=J, G=G, act=t["cur_act"], ref_group=t["cur_nxt"], skipmask=self.skipmask,
+                _fill(icp_arr[lv], self.keep, J=J, G=G, act=t["cur_act"], ref_group=t["cur_grp"],
+                      ref_group_all=t["cur_grp_all"], skipmask=self.skipmask,
                       ref_off=d["rv_off"], g_inst=g_inst, ref_table=d["table"], ref_H=d["H"], ref_pts=d["rv"],
-                      mov_H=Hm, mv=self.mv, mv_gid=self.mv_gid, mv_inst=self.mv_inst,
-                      n_mv=self.sampler.t["ctr"][1:], vdeg=t["vdeg"], lo=lo, cs=d["cs"], radius=self.radius[lv], df=0,
+                      mov_H=Hm, mv=self.mv, mv_gid=self.mv_gid, mv_inst=self.mv_inst, mv_cap=M,
+                      n_mv=self.sampler.t["ctr"][1:], vdeg=t["vdeg"], lo=lo, cs=d["cs"], rings=ICP_RINGS,
+                      radius=self.radius[lv], df=0,
                       angle_reg=self.angle_reg, max_iter=80, stopping_delta=self.stopping_delta[lv], want_l1=0,
-                      want_ratio=0, nn_bwd=nn_bwd, T=t["T"], l1_err=t["l1_err"], ratio=t["ratio"], **sc)
+                      want_ratio=0, nn_bwd=nn_bwd, T=t["T"], l1_err=t["l1_err"], ratio=t["ratio"], prof=self.prof[lv], **sc)
             self.icp_arr = icp_arr
 
     # ----------------------------------------------------------------------------------------------------------

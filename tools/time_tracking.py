@@ -38,12 +38,16 @@ def main():
             return out
 
         mod.forward = wrapped
-    ops.reset_launch_count()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    model(batch)
-    torch.cuda.synchronize()
-    total = time.perf_counter() - t0
+    reps = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    for _ in range(reps):
+        times.clear()
+        ops.reset_launch_count()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        model(batch)
+        torch.cuda.synchronize()
+        total = time.perf_counter() - t0
+        print(f"total={total:.3f}s stages={ {k: round(v, 3) for k, v in times.items()} }", flush=True)
     seq = model.forward_dict["sequences"][0]
     res = seq.get("tracking_results", {})
     n_ex = sum(int(v["fxyz"].shape[0]) for v in res.values())
