@@ -204,30 +204,6 @@ int pcs_l1_heightfield(pcs_stream_t s, const float *min_z, const float *weight, 
                        int Y, float lr, float lr_gamma, int decay_step, float rigid_weight, int max_iters,
                        int32_t *info, float *loss_out);
 
-/* ---- per-cluster registration ------------------------------------------------------------------
- * Replaces register_to_next_frame (pcdet/models/registration/preprocessors/registration_utils.py:83-206): the
- * whole trimmed two-way ICP loop (<= max_iter iterations; forward + backward K=1 radius graphs, per-component
- * fp64 centroids / covariance, rotation regulariser, 3x3 SVD rotation, transform accumulation, point update,
- * 3-strike loss stopping rule), the truncated-mean residual of the last iteration and the matched-fraction
- * count, in ONE persistent cooperative launch.
- *   geo_lo f32[4], geo_dims i64[4] (device, from pcs_grid_params with pad > 0), geo_vs (host) f32[4]
- *   ref_* : static grid (pcs_hash_build, same geometry) over the non-stationary ref points `ref` f32[nr][4]
- *   all_* : static grid over ALL ref points (stationary included) for the matched-fraction graph
- *   mov_* : scratch for the moving grid (table[mov_H], sorted f32[nm][4], sidx i32[nm]); counters i32[4]
- *   mov f32[nm][4] non-stationary moving points, UPDATED IN PLACE; mov_comp i32[nm] in [0, C)
- *   df = ref frame - moving frame; radius = sqrt(r^2 + df^2) as fp32
- *   scratch: nn_fwd i32[nm], nn_bwd i32[nr], mom f64[C][17] (zero), Ti f64[C][12], mu f64[C][6], l1_sum f64[C][2]
- *   state f64[4] = {1e10, 0, 0, 0}, istate i32[4] = {3, 0, 0, 0}; istate[1] returns the iterations run
- *   T f64[C][12] in/out (R row-major then t; identity on entry), l1_err f64[C] out, match_cnt i32[C] (zero) out */
-int pcs_register_icp(pcs_stream_t s, const float *geo_lo, const float *geo_vs, const int64_t *geo_dims,
-                     const pcs_slot_t *ref_table, int64_t ref_H, const float *ref_sorted, const int32_t *ref_sidx,
-                     const pcs_slot_t *all_table, int64_t all_H, const float *all_sorted, const int32_t *all_sidx,
-                     pcs_slot_t *mov_table, int64_t mov_H, float *mov_sorted, int32_t *mov_sidx, int32_t *counters,
-                     float *mov, const int32_t *mov_comp, const float *ref, int nm, int nr, int C, int df, float radius,
-                     double angle_reg, int max_iter, double stopping_delta, int32_t *nn_fwd, int32_t *nn_bwd,
-                     double *mom, double *Ti, double *T, double *mu, double *l1_sum, double *state, int32_t *istate,
-                     double *l1_err, int32_t *match_cnt);
-
 /* Curvature pruning of plane centres ("Truncated Least Squares", preprocessor_utils.py:175-193): for every threshold
  * (descending), kNN (self included) mean curvature of the surviving planes; planes with curvature >= threshold are
  * dropped whenever threshold <= max curvature.  One cooperative launch (grid barriers only around rounds that remove

@@ -529,73 +529,19 @@ def l1_heightfield(min_z, weight, lr, decay_steps, rigid_weight, max_iters, lr_g
     return h, info
 
 
-ICP_PAD_CELLS = 8
-
-
 def register_icp(mov_fxyz, mov_comp, mov_stationary, ref_fxyz, ref_stationary, num_components, radius, frame_offset,
                  angle_regularizer=10.0, max_iter=20, stopping_delta=5e-2):
-    """register_to_next_frame (registration_utils.py:83-206) in one persistent launch.
+    """register_to_next_frame (registration_utils.py:83-206) in one persistent launch (the batched tracker kernel of
+    csrc/track.cu with a batch of one instance).
 
     mov_fxyz f32[vm,4] / mov_comp int[vm] / mov_stationary bool[vm]: the moving (down-sampled) frame;
     ref_fxyz f32[vr,4] / ref_stationary bool[vr]: the target frame; frame_offset = ref frame - moving frame.
     Returns (moved_fxyz f32[vm,4], T f64[C,4,4], l1_component_error f64[C], comp_edge_ratio f32[C], info) where
     info is an int32[4] device tensor whose entry 1 is the number of iterations run.
     """
-    mov_fxyz = _as_points(mov_fxyz, "moving.fxyz")
-    ref_all = _as_points(ref_fxyz, "ref.fxyz")
-    dev = mov_fxyz.device
-    C = int(num_components)
-    L = _lib.lib()
-    df = int(frame_offset)
-    r_eff = float(np.float32((float(radius) ** 2 + df ** 2) ** 0.5))  # :111-112
-    mov_comp = mov_comp.long()
-    comp_deg = torch.bincount(mov_comp, minlength=C).float()  # :113-114
-    ns_m = ~mov_stationary.bool()
-    ns_r = ~ref_stationary.bool()
-    mov = mov_fxyz[ns_m].contiguous()
-    comp = mov_comp[ns_m].int().contiguous()
-    any_stat_ref = bool(ref_stationary.any().item())
-    ref = ref_all[ns_r].contiguous() if any_stat_ref else ref_all
-    nm, nr = mov.shape[0], ref.shape[0]
-    T = torch.zeros(C, 12, dtype=torch.float64, device=dev)
-    T[:, 0] = T[:, 4] = T[:, 8] = 1.0
-    l1 = torch.zeros(C, dtype=torch.float64, device=dev)
-    match = torch.zeros(C, dtype=torch.int32, device=dev)
-    istate = torch.tensor([3, 0, 0, 0], dtype=torch.int32, device=dev)
-    if nm > 0 and ref_all.shape[0] > 0:
-        vs = radius_voxel_size(r_eff)
-        grid_all = CellGrid(ref_all, vs, bounds_sets=[ref_all, mov_fxyz], pad=ICP_PAD_CELLS)
-        grid_ref = grid_all if not any_stat_ref else CellGrid(ref if nr > 0 else ref_all[:0], vs,
-                                                              geometry=(grid_all.seg_lo, grid_all.seg_dims))
-        H = next_pow2(max(2 * nm, 1024))
-        mov_table = torch.empty(H, 4, dtype=torch.int32, device=dev)
-        mov_sorted = torch.empty(nm, 4, dtype=torch.float32, device=dev)
-        mov_sidx = torch.empty(nm, dtype=torch.int32, device=dev)
-        counters = torch.zeros(4, dtype=torch.int32, device=dev)
-        nn_fwd = torch.empty(nm, dtype=torch.int32, device=dev)
-        nn_bwd = torch.empty(max(nr, 1), dtype=torch.int32, device=dev)
-        mom = torch.zeros(C, 17, dtype=torch.float64, device=dev)
-        Ti = torch.zeros(C, 12, dtype=torch.float64, device=dev)
-        mu = torch.zeros(C, 6, dtype=torch.float64, device=dev)
-        l1_sum = torch.zeros(C, 2, dtype=torch.float64, device=dev)
-        state = torch.tensor([1e10, 0.0, 0.0, 0.0], dtype=torch.float64, device=dev)
-        with torch.cuda.device(dev), _timed("register_icp", nm=nm, nr=nr, C=C):
-            _lib.check(L.pcs_register_icp(
-                _stream(), _ptr(grid_all.seg_lo), _f4(vs), _ptr(grid_all.seg_dims), _ptr(grid_ref.table), grid_ref.H,
-                _ptr(grid_ref.sorted_pts), _ptr(grid_ref.sorted_idx), _ptr(grid_all.table), grid_all.H,
-                _ptr(grid_all.sorted_pts), _ptr(grid_all.sorted_idx), _ptr(mov_table), H, _ptr(mov_sorted),
-                _ptr(mov_sidx), _ptr(counters), _ptr(mov), _ptr(comp), _ptr(ref), nm, nr, C, df, r_eff,
-                float(angle_regularizer), int(max_iter), float(stopping_delta), _ptr(nn_fwd), _ptr(nn_bwd), _ptr(mom),
-                _ptr(Ti), _ptr(T), _ptr(mu), _ptr(l1_sum), _ptr(state), _ptr(istate), _ptr(l1), _ptr(match)),
-                "pcs_register_icp")
-    moved = mov_fxyz.clone()
-    moved[ns_m] = mov
-    T44 = torch.zeros(C, 4, 4, dtype=torch.float64, device=dev)
-    T44[:, :3, :3] = T[:, :9].reshape(C, 3, 3)
-    T44[:, :3, 3] = T[:, 9:]
-    T44[:, 3, 3] = 1.0
-    ratio = match.float() / (comp_deg + 1e-6)  # :199
-    return moved, T44, l1, ratio, istate
+    from .tracker import register_pair
+    return register_pair(mov_fxyz, mov_comp, mov_stationary, ref_fxyz, ref_stationary, num_components, radius,
+                         frame_offset, angle_regularizer, max_iter, stopping_delta)
 
 
 def cluster_labels_multi(fxyz, radii, max_num_neighbors=32, chunk=10, num_frames=None):

@@ -523,3 +523,91 @@ class TrackBatch:
         T[loc, :, :3, :3] = tr[:, :, :9].reshape(-1, nf, 3, 3)
         T[loc, :, :3, 3] = tr[:, :, 9:]
         return T
+
+
+def register_pair(mov_fxyz, mov_comp, mov_stationary, ref_fxyz, ref_stationary, num_components, radius, frame_offset,
+                  angle_regularizer=10.0, max_iter=20, stopping_delta=5e-2):
+    """register_to_next_frame (registration_utils.py:83-206) for ONE (moving, target) pair on the batched ICP kernel
+    (a batch of one instance).  Same contract as ops.register_icp."""
+    L = _lib.lib()
+    mov_fxyz = mov_fxyz.float().contiguous()
+    ref_fxyz = ref_fxyz.float().contiguous()
+    dev = mov_fxyz.device
+    if not mov_fxyz.is_cuda:
+        raise _lib.PcsError("register_pair: CUDA tensors required (no CPU path exists)")
+    C = int(num_components)
+    df = int(frame_offset)
+    mov_comp = mov_comp.long().reshape(-1)
+    ns_m = ~mov_stationary.bool().reshape(-1)
+    ns_r = ~ref_stationary.bool().reshape(-1)
+    keep = {}
+    T = torch.zeros(C, 12, dtype=torch.float64, device=dev)
+    T[:, 0] = T[:, 4] = T[:, 8] = 1.0
+    l1 = _z(C, torch.float64, dev)
+    ratio = _z(C, torch.float32, dev)
+    iters = _z(1, torch.int32, dev)
+    moved = mov_fxyz.clone()
+    nm = int(ns_m.sum().item())
+    if nm > 0 and ref_fxyz.shape[0] > 0:
+        with torch.cuda.device(dev):
+            s = _stream()
+            # moving voxels grouped by component
+            idx_m = ns_m.nonzero().reshape(-1)
+            o = torch.argsort(mov_comp[idx_m], stable=True)
+            idx_m = idx_m[o]
+            mv = mov_fxyz[idx_m].contiguous()
+            mv_gid = mov_comp[idx_m].int().contiguous()
+            mv_inst = _z(nm, torch.int32, dev)
+            n_mv = torch.tensor([nm], dtype=torch.int32, device=dev)
+            vdeg = torch.bincount(mov_comp, minlength=C).int().contiguous()
+            # reference grid: group 0 = non-stationary voxels (ICP targets), group 1 = all voxels (matched fraction)
+            both = torch.cat([ref_fxyz[ns_r], ref_fxyz])
+            lo = (torch.cat([ref_fxyz[:, 1:], mov_fxyz[:, 1:]]).min(0)[0] - 32.0).tolist()
+            grp = torch.cat([_z(int(ns_r.sum().item()), torch.int32, dev),
+                             torch.ones(ref_fxyz.shape[0], dtype=torch.int32, device=dev)])
+            cs = float(radius) * 1.001
+            lo_c = (ctypes.c_double * 3)(*lo)
+            n_ref = int(both.shape[0])
+            keys = _e(n_ref, torch.int64, dev)
+            _lib.check(L.pcs_trk_cell_keys(s, _ptr(both.contiguous()), _ptr(grp), n_ref, lo_c, cs, _ptr(keys)),
+                       "pcs_trk_cell_keys")
+            ks, perm = torch.sort(keys)
+            rv = both[perm].contiguous()
+            rv[:, 0] = 0.0  # payload bits: nothing to skip
+            uk, cnt = torch.unique_consecutive(ks, return_counts=True)
+            starts = (cnt.cumsum(0) - cnt).int().contiguous()
+            Hc = next_pow2(max(2 * int(uk.shape[0]), 1024))
+            table = _e((Hc, 4), torch.int32, dev)
+            err = _z(1, torch.int32, dev)
+            _lib.check(L.pcs_trk_grid_fill(s, _ptr(table), Hc, _ptr(uk), _ptr(starts), _ptr(cnt.int().contiguous()),
+                                           int(uk.shape[0]), _ptr(err)), "pcs_trk_grid_fill")
+            n_ns = int(ns_r.sum().item())
+            ref_off = torch.tensor([0, n_ns, n_ref], dtype=torch.int32, device=dev)
+            Hm = next_pow2(max(2 * nm, 1024))
+            sc = dict(mov_table=_e((Hm, 4), torch.int32, dev), mov_sorted=_e((nm, 4), torch.float32, dev),
+                      mov_sidx=_e(nm, torch.int32, dev), mov_cells=_e(nm, torch.int32, dev), mov_ctr=_z(4, torch.int32, dev),
+                      nn_fwd=_e(nm, torch.int32, dev), nn_bwd=_e(max(n_ns, 1), torch.int32, dev),
+                      boff=_z(2, torch.int32, dev), mvbeg=_z(1, torch.int32, dev), mvend=_z(1, torch.int32, dev),
+                      mom=_z((C, 17), torch.float64, dev), Ti=_z((C, 12), torch.float64, dev),
+                      mu=_z((C, 6), torch.float64, dev), l1_sum=_z((C, 2), torch.float64, dev), l1_n=_z(C, torch.float64, dev),
+                      phase=_z(1, torch.int32, dev), cd=_z(1, torch.int32, dev), iters=iters,
+                      itcnt=_z((int(max_iter) + 2) * 2, torch.int32, dev), last=_z(1, torch.float64, dev),
+                      loss=_z(1, torch.float64, dev), match_cnt=_z(C, torch.int32, dev))
+            _lib.check(L.pcs_trk_table_clear(s, _ptr(sc["mov_table"]), Hm, _ptr(sc["mov_ctr"])), "pcs_trk_table_clear")
+            st = IcpStruct()
+            r_eff = float(np.float32((float(radius) ** 2 + df ** 2) ** 0.5))  # :111-112
+            _fill(st, keep, J=1, G=C, act=torch.ones(1, dtype=torch.int32, device=dev), ref_group=_z(1, torch.int32, dev),
+                  ref_group_all=torch.ones(1, dtype=torch.int32, device=dev), skipmask=_z(1, torch.int32, dev),
+                  ref_off=ref_off, g_inst=_z(C, torch.int32, dev), ref_table=table, ref_H=Hc, ref_pts=rv, mov_H=Hm, mv=mv,
+                  mv_gid=mv_gid, mv_inst=mv_inst, n_mv=n_mv, mv_cap=nm, vdeg=vdeg, lo=lo, cs=cs, rings=1, radius=r_eff,
+                  df=df, angle_reg=float(angle_regularizer), max_iter=int(max_iter),
+                  stopping_delta=float(stopping_delta), want_l1=1, want_ratio=1, T=T, l1_err=l1, ratio=ratio,
+                  prof=None, **sc)
+            _lib.check(L.pcs_trk_icp(s, ctypes.byref(st)), "pcs_trk_icp")
+            moved[idx_m] = mv
+    T44 = torch.zeros(C, 4, 4, dtype=torch.float64, device=dev)
+    T44[:, :3, :3] = T[:, :9].reshape(C, 3, 3)
+    T44[:, :3, 3] = T[:, 9:]
+    T44[:, 3, 3] = 1.0
+    info = torch.stack([_z(1, torch.int32, dev)[0], iters[0], _z(1, torch.int32, dev)[0], _z(1, torch.int32, dev)[0]])
+    return moved, T44, l1, ratio, info
