@@ -284,7 +284,9 @@ typedef struct {
   void *last, *loss;                      /* double[J] */
   void *match_cnt;                        /* int32[G] */
   void *l1_err, *ratio;                   /* double[G], float[G] outputs (want_l1 / want_ratio) */
-  void *prof;                             /* optional int64[16] += ns per phase (B C D E F G H tail), [8] iterations, [9] launches */
+  void *prof;                             /* optional int64[256] += ns per phase (B C D E F G H tail), [8] iterations,
+                                             [9] launches, [13] / [14] moving / reference voxels searched (summed over
+                                             iterations), [16..] per-iteration search ns, [112..] active queries */
 } pcs_trk_icp_t;
 
 typedef struct {
@@ -324,6 +326,9 @@ int pcs_trk_sampler_init(pcs_stream_t s, const pcs_trk_sampler_t *S);
 int pcs_trk_sample(pcs_stream_t s, const pcs_trk_sampler_t *S);
 /* register_to_next_frame for all instances in one persistent cooperative launch. */
 int pcs_trk_icp(pcs_stream_t s, const pcs_trk_icp_t *P);
+/* CUDA-event timing of the ICP launches: enable / reset, then read (count, summed ms; synchronises on the events). */
+void pcs_trk_icp_timing(int enable);
+int pcs_trk_icp_elapsed(double *total_ms);
 int pcs_trk_dir_init(pcs_stream_t s, const pcs_trk_ctx_t *C);
 int pcs_trk_step(pcs_stream_t s, const pcs_trk_ctx_t *C, const pcs_trk_sampler_t *S, const pcs_trk_icp_t *levels,
                  int n_levels, int t);

@@ -73,6 +73,8 @@ _SIGNATURES = {
     "pcs_trk_sampler_init": (c_int, [c_void_p, c_void_p]),
     "pcs_trk_sample": (c_int, [c_void_p, c_void_p]),
     "pcs_trk_icp": (c_int, [c_void_p, c_void_p]),
+    "pcs_trk_icp_timing": (None, [c_int]),
+    "pcs_trk_icp_elapsed": (c_int, [c_void_p]),
     "pcs_trk_dir_init": (c_int, [c_void_p, c_void_p]),
     "pcs_trk_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int]),
     "pcs_trk_finish": (c_int, [c_void_p, c_void_p, c_void_p]),
@@ -107,6 +109,9 @@ def lib():
             fn.argtypes = args
         _lib = L
     return _lib
+
+
+PCS_ERR_BAD_ARG, PCS_ERR_TABLE_FULL, PCS_ERR_KEY_RANGE = -2, -3, -4  # include/pcseq_b200.h
 
 
 class PcsError(RuntimeError):

@@ -73,7 +73,8 @@ radius_search_kernel(const pcs_slot_t *__restrict__ table, long long mask, const
                      const int *__restrict__ sorted_idx, SegGeom g, const float4 *__restrict__ queries,
                      long long m, const int *__restrict__ order, QueryRange qr, const float *__restrict__ radius,
                      float radius_scalar, int K, int *__restrict__ nbr_idx, float *__restrict__ nbr_d2,
-                     int *__restrict__ nbr_cnt, UfTargets uf, const int *__restrict__ skip_full_cnt,
+                     int *nbr_cnt, UfTargets uf, const int *skip_full_cnt,  // may alias (cascade passes): no __restrict__
+                    
                      const unsigned int *__restrict__ occ, int occ_shift) {
   __shared__ float4 s_lo[PCS_MAX_SEGMENTS];
   __shared__ long long s_dims[PCS_MAX_SEGMENTS * 4];

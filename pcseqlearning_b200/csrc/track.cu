@@ -22,6 +22,9 @@
 #include <cooperative_groups.h>
 #include <stdlib.h>
 
+#include <utility>
+#include <vector>
+
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
@@ -892,6 +895,16 @@ __global__ void __launch_bounds__(kTrkThreads, kMinBlocks) trk_icp_kernel(IcpB A
       s_aoff[A.J] = o;
     }
     __syncthreads();
+    if (A.prof && tid == 0) {
+      long long nf = 0, nb = 0;
+      for (int jj = 0; jj < A.J; jj++)
+        if (A.phase[jj] == PH_RUN) {
+          nf += A.mvend[jj] - A.mvbeg[jj];
+          nb += A.boff[jj + 1] - A.boff[jj];
+        }
+      A.prof[13] += nf;
+      A.prof[14] += nb;
+    }
     const int n_active = s_aoff[A.J];
     const int BQ = A.batch;  // work items per warp batch (<= 32)
     const long long nbatch = ((long long)n_active + BQ - 1) / BQ;
@@ -1956,6 +1969,10 @@ int pcs_trk_sample(pcs_stream_t s, const pcs_trk_sampler_t *S) {
   return 0;
 }
 
+// optional CUDA-event timing of the ICP launches (bench.py's roofline leg)
+static bool g_icp_timing = false;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_icp_events;
+
 static int launch_icp(cudaStream_t st, const pcs_trk_icp_t *P) {
   if (!P || P->J < 1 || P->G < 1 || P->max_iter < 1 || (P->ref_H & (P->ref_H - 1)) || (P->mov_H & (P->mov_H - 1)) ||
       P->ref_H < 2 || P->mov_H < 2 || !P->mv || !P->n_mv || !P->ref_pts || ((uintptr_t)P->mv & 15) ||
@@ -1975,13 +1992,45 @@ static int launch_icp(cudaStream_t st, const pcs_trk_icp_t *P) {
   const void *kern = occ >= 4 ? (const void *)trk_icp_kernel<4> : (occ == 3 ? (const void *)trk_icp_kernel<3> : (const void *)trk_icp_kernel<2>);
   const int blocks = coop_grid(kern, kTrkThreads, 1LL << 40, occ >= 4 ? 4 : (occ == 3 ? 3 : 2));
   void *args[] = {&A};
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (g_icp_timing) {
+    cudaEventCreate(&ev0);
+    cudaEventCreate(&ev1);
+    cudaEventRecord(ev0, st);
+  }
   cudaError_t e = cudaLaunchCooperativeKernel(kern, dim3((unsigned)blocks), dim3(kTrkThreads), args, 0, st);
+  if (g_icp_timing) {
+    cudaEventRecord(ev1, st);
+    g_icp_events.emplace_back(ev0, ev1);
+  }
   g_launches++;
   if (e != cudaSuccess) return set_error((int)e, "trk_icp_kernel (cooperative launch)");
   return check_launch("trk_icp_kernel");
 }
 
 int pcs_trk_icp(pcs_stream_t s, const pcs_trk_icp_t *P) { return launch_icp(as_stream(s), P); }
+
+void pcs_trk_icp_timing(int enable) {
+  g_icp_timing = enable != 0;
+  for (auto &p : g_icp_events) {
+    cudaEventDestroy(p.first);
+    cudaEventDestroy(p.second);
+  }
+  g_icp_events.clear();
+}
+
+/* Synchronises on the recorded events; returns the number of timed ICP launches and their summed duration. */
+int pcs_trk_icp_elapsed(double *total_ms) {
+  double t = 0.0;
+  for (auto &p : g_icp_events) {
+    cudaEventSynchronize(p.second);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, p.first, p.second);
+    t += ms;
+  }
+  if (total_ms) *total_ms = t;
+  return (int)g_icp_events.size();
+}
 
 int pcs_trk_dir_init(pcs_stream_t s, const pcs_trk_ctx_t *C) {
   if (!C || C->J < 1 || C->G < 1 || C->M < 1) return set_error(PCS_ERR_BAD_ARG, "pcs_trk_dir_init: bad args");

@@ -321,8 +321,12 @@ def compact_grid(points, voxel_size, **kw):
     if GRID_SORTED:
         kw = dict(kw, sorted_cells=True)
     grid = CellGrid(points, voxel_size, table_size=small, **kw)
-    if grid.counters[2].item() != 0:
+    code = int(grid.counters[2].item())
+    if code == _lib.PCS_ERR_TABLE_FULL:
         grid = CellGrid(points, voxel_size, **kw)
+        code = int(grid.counters[2].item())
+    if code != 0:  # key range overflow etc.: a rebuild cannot help
+        raise _lib.PcsError(f"voxel hash build failed on device (code {code})")
     return grid
 
 
@@ -600,9 +604,9 @@ def group_minmax(values, ids, num_groups):
 def gather_rows(src, idx):
     """src[idx] for a contiguous tensor whose rows are 1, 4, 8, 12 or 16 bytes (anything else falls back to torch
     indexing).  idx: int64 row indices."""
-    if not src.is_cuda or not src.is_contiguous() or src.dim() == 0:
+    if not src.is_cuda or not src.is_contiguous() or src.dim() == 0 or src.shape[0] == 0 or idx.numel() == 0:
         return src[idx]
-    row_bytes = src.element_size() * (src[0].numel() if src.dim() > 1 else 1)
+    row_bytes = src.element_size() * int(np.prod(src.shape[1:])) if src.dim() > 1 else src.element_size()
     if row_bytes not in (1, 4, 8, 12, 16) or (row_bytes == 16 and src.data_ptr() % 16):
         return src[idx]
     idx = idx.long().contiguous()

@@ -11,7 +11,7 @@ import numpy as np
 import torch
 from torch import nn
 
-from .. import graph_utils, ops
+from .. import _lib, graph_utils, ops
 from ..grid_sampling import GridSampling3D
 from ..utils import EasyDict, Timer, filter_dict
 from ..utils.scatter import scatter_max, scatter_min
@@ -85,7 +85,11 @@ def smooth_velo(_comp_velos, comp_center_diffs, frame_id, next_frame_id, weight0
     if frame_id > next_frame_id:
         frame_id, next_frame_id = next_frame_id, frame_id
     n_opt = _comp_velos.shape[0] * (next_frame_id - frame_id + 1) * 2
-    if use_kernels and _comp_velos.is_cuda and _comp_velos.is_contiguous() and n_opt <= ops.SMOOTH_VELO_MAX:
+    if use_kernels and _comp_velos.is_cuda:
+        if not (_comp_velos.is_contiguous() and n_opt <= ops.SMOOTH_VELO_MAX):
+            # sequential mirror only (the product path is tracker.TrackBatch, whose smoothing kernel has no such
+            # limit); no silent eager fallback
+            raise _lib.PcsError(f"smooth_velo kernel limit exceeded: {n_opt} optimised values (<= {ops.SMOOTH_VELO_MAX})")
         # the whole optimisation (<= 300 AdamW steps + stopping rule) in one single-CTA launch, in place like the
         # reference's nn.Parameter that shares storage with the tensor
         ops.smooth_velo(_comp_velos, comp_center_diffs, frame_id, next_frame_id, weight0, weight, num_itr, stopping)

@@ -11,7 +11,7 @@ torch programs on a few thousand cells (SURVEY.md section 8f ranks moving them i
 import numpy as np
 import torch
 
-from .. import ops
+from .. import _lib, ops
 from ..utils import EasyDict
 from ..utils.scatter import scatter_count, scatter_max, scatter_mean, scatter_min, scatter_sum
 
@@ -124,8 +124,13 @@ def compute_min_height_from_ransac(pillar_dims, num_pillars, voxels, pillars, cf
     xyz, normal = best_center, best_normal
     K = cfg.K
     thresholds = np.logspace(np.log(5) / np.log(10), np.log(0.01) / np.log(10), 100)
-    if use_kernels and K <= xyz.shape[0] <= ops.PRUNE_MAX_PLANES and K <= 16:
-        keep = ops.plane_prune(xyz, normal, K, thresholds)  # the whole 100-threshold loop in one launch
+    if use_kernels:
+        # the whole 100-threshold loop in one launch; there is no silent eager fallback: sizes outside the kernel's
+        # limits are an error (use_kernels=False is the torch mirror kept for the tests)
+        if not (K <= xyz.shape[0] <= ops.PRUNE_MAX_PLANES and K <= 16):
+            raise _lib.PcsError(f"plane pruning kernel limits exceeded: {xyz.shape[0]} planes (K <= n <= "
+                                f"{ops.PRUNE_MAX_PLANES}), K = {K} (<= 16)")
+        keep = ops.plane_prune(xyz, normal, K, thresholds)
         xyz, normal = xyz[keep], normal[keep]
         thresholds = []
     for threshold in thresholds:
@@ -161,7 +166,10 @@ def compute_min_height_from_ransac(pillar_dims, num_pillars, voxels, pillars, cf
 def l1_minimization(pillars, pillar_dims, cfg, max_countdown=3, use_kernels=True):
     """AdamW L1 smoothing of the pillar height grid (preprocessor_utils.py:313-350)."""
     X, Y = pillar_dims
-    if use_kernels and X * Y <= ops.L1_MAX_CELLS and X >= 3 and Y >= 3 and len(cfg.DECAY_STEPS) <= 1:
+    if use_kernels:
+        if not (X * Y <= ops.L1_MAX_CELLS and X >= 3 and Y >= 3 and len(cfg.DECAY_STEPS) <= 1):
+            raise _lib.PcsError(f"L1 height-field kernel limits exceeded: grid {X} x {Y} (3 <= X, Y; X * Y <= "
+                                f"{ops.L1_MAX_CELLS}), {len(cfg.DECAY_STEPS)} LR milestones (<= 1)")
         # the whole optimisation (<= MAX_NUM_ITERS AdamW steps + stopping rule) in one single-CTA launch
         pillars["height"], pillars["l1_info"] = ops.l1_heightfield(pillars.min_z, pillars.weight, cfg.LR,
                                                                    list(cfg.DECAY_STEPS), cfg.RIGID_WEIGHT,

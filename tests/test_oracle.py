@@ -168,3 +168,44 @@ def test_ground_oracle_matches_reference_python(golden_dir):
     assert np.mean(np.abs(pmz - g["pillar_min_z"]) < 2e-2) > 0.98
     assert np.mean(np.abs(ph - g["pillar_height"]) < 3e-2) > 0.97
     assert np.mean((height < 0.5) == (g["height"] < 0.5)) > 0.995
+
+
+def test_tracking_oracle_matches_reference_python(golden_dir):
+    """oracle/tracking_np.track_frame against the golden recorded from the reference's own track_frame."""
+    from oracle import tracking_np as trk
+    g = np.load(os.path.join(golden_dir, "tracking.npz"))
+    pts, comp = g["points"], g["component"]
+    n_comp = int(comp.max()) + 1
+    diam = trk.component_diameter(pts[:, 1:], comp, n_comp)[comp]
+    trace = []
+    ex = trk.track_frame(pts, g["sweep"], comp, diam > 12.5, int(g["anchor"]), trk.tracking_cfg(), trace=trace)
+    assert len(trace) == 48
+    got_c, want_c = set(np.unique(ex["component"]).tolist()), set(np.unique(g["ex_component"]).tolist())
+    assert len(got_c & want_c) / len(got_c | want_c) > 0.97
+    pair = lambda o, c: set((np.asarray(o, np.int64) * 100000 + np.asarray(c, np.int64)).tolist())
+    got_p, want_p = pair(ex["original_indices"], ex["component"]), pair(g["ex_original_indices"], g["ex_component"])
+    assert len(got_p & want_p) / len(got_p | want_p) > 0.98
+    both = sorted(got_c & want_c)
+    dT = np.abs(ex["transforms"][both] - g["transforms"][both])
+    assert np.median(dT[..., :3, :3].max((-1, -2))) < 1e-4
+
+
+def test_eval_oracle_matches_reference_python(golden_dir):
+    """evaluate_proposal / extract_traces restatements against the reference-Python goldens."""
+    from oracle import tracking_np as trk
+    g = np.load(os.path.join(golden_dir, "eval_tracking.npz"))
+    keep = g["seg_all"] < 17
+    ev = trk.evaluate_proposal(g["points_all"][keep], [g["comp_rad1x25"], g["comp_rad0x75"], g["comp_rad0x25"]],
+                               g["box_gt_box_attr"], g["box_gt_box_frame"], g["box_gt_box_track_label"])
+    for k in ["point_gt_box_id", "point_gt_trace_id", "point_pred_trace_id", "point_pred_box_id"]:
+        np.testing.assert_array_equal(ev[k], g[f"eval_{k}"], err_msg=k)
+    np.testing.assert_allclose(ev["gt_box_best_iou"], g["eval_gt_box_best_iou"], atol=1e-6)
+    np.testing.assert_allclose(ev["gt_trace_best_iou"], g["eval_gt_trace_best_iou"], atol=1e-6)
+    am = g["height_all"] > 0
+    ex = {k: g[f"ex_{k}"] for k in ["fxyz", "component", "moving"]}
+    best = np.zeros(g["box_gt_box_attr"].shape[0], np.float32)
+    full = trk.extract_traces(g["points_all"][am], g["sweep_all"][am], ex, g["box_gt_box_attr"], g["box_gt_box_frame"],
+                              best, 0.5)
+    for k in ["fxyz", "component", "original_indices", "frame_indices", "moving", "component_hit", "component_size"]:
+        np.testing.assert_array_equal(full[k], g[f"full_{k}"], err_msg=k)
+    np.testing.assert_allclose(best, g["best_iou_after_tracking"], atol=1e-6)
