@@ -47,6 +47,8 @@ struct PGrid {
   int *sidx;          // original row of every sorted row (nullptr = identity)
   int *cells;         // slots claimed by the current build
   int *ctr;           // [0] claimed cells, [1] scatter cursor, [2] error flag
+  const int *tie;     // optional per-row tie-break key (component id): equal distances are resolved by (tie, row)
+                      // instead of the row index alone -- row order of the moving voxels is not reproducible
   float lo0, lo1, lo2, inv_cs, cs;
 };
 
@@ -152,9 +154,39 @@ __device__ __forceinline__ float dist2_acc(float acc, float rx, float ry, float 
 // query; cells are visited in ascending lower bound and pruned against the best distance found so far.  Rows whose
 // payload has a bit of `skipmask` set are ignored.  Returns the row's original index (warp-uniform) or -1; ties by
 // ascending index.
+// one cell swept by the warp, 32 rows per step; (best, bidx, bound) are warp-uniform on entry and on return
+__device__ __forceinline__ void nn_sweep(const PGrid &g, int cs, int cc, float qx, float qy, float qz, float acc0,
+                                         unsigned int skipmask, int lane, unsigned long long &best, unsigned int &bidx,
+                                         float &bound) {
+  for (int j = lane; j < cc; j += 32) {
+    const float4 p = g.sorted[cs + j];
+    if (__float_as_uint(p.x) & skipmask) continue;
+    const float d2 = dist2_acc(acc0, p.y, p.z, p.w, qx, qy, qz);
+    if (d2 <= bound) {
+      const unsigned int idx = g.sidx ? (unsigned int)g.sidx[cs + j] : (unsigned int)(cs + j);
+      const unsigned long long k =
+          ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned int)(g.tie ? g.tie[idx] : (int)idx);
+      if (k < best || (k == best && idx < bidx)) {
+        best = k;
+        bidx = idx;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long t = __shfl_xor_sync(kAll, best, o);
+    const unsigned int ti = __shfl_xor_sync(kAll, bidx, o);
+    if (t < best || (t == best && ti < bidx)) {
+      best = t;
+      bidx = ti;
+    }
+  }
+  if (best != ~0ull) bound = fminf(bound, __uint_as_float((unsigned int)(best >> 32)));
+}
+
 __device__ int nn_search(const PGrid &g, bool cursor_mode, int group, float qx, float qy, float qz, float acc0,
                          float r2, unsigned int skipmask, int lane, float *d2_out = nullptr,
-                         unsigned long long best0 = ~0ull) {
+                         unsigned long long best0 = ~0ull, unsigned long long *key_out = nullptr) {
   const float ux = cell_u(qx, g.lo0, g.inv_cs), uy = cell_u(qy, g.lo1, g.inv_cs), uz = cell_u(qz, g.lo2, g.inv_cs);
   const float fx = floorf(ux), fy = floorf(uy), fz = floorf(uz);
   const int cx = clamp_cell((int)fx), cy = clamp_cell((int)fy), cz = clamp_cell((int)fz);
@@ -186,7 +218,13 @@ __device__ int nn_search(const PGrid &g, bool cursor_mode, int group, float qx, 
       }
     }
   }
-  unsigned long long best = best0;
+  // candidates are ordered by (d2, tie key, row); with g.tie == nullptr the tie key is the row itself
+  unsigned long long best = ~0ull;
+  unsigned int bidx = 0xffffffffu;
+  if (best0 != ~0ull) {
+    bidx = (unsigned int)(best0 & 0xffffffffu);
+    best = (best0 & 0xffffffff00000000ull) | (unsigned int)(g.tie ? g.tie[bidx] : (int)bidx);
+  }
   float bound = r2;
   while (true) {
     const unsigned int pick = __reduce_min_sync(kAll, sel);
@@ -195,34 +233,19 @@ __device__ int nn_search(const PGrid &g, bool cursor_mode, int group, float qx, 
     const int src = pick & 31;
     if (lane == src) sel = 0xffffffffu;
     const int cs = __shfl_sync(kAll, start, src), cc = __shfl_sync(kAll, count, src);
-    for (int j = lane; j < cc; j += 32) {
-      const float4 p = g.sorted[cs + j];
-      if (__float_as_uint(p.x) & skipmask) continue;
-      const float d2 = dist2_acc(acc0, p.y, p.z, p.w, qx, qy, qz);
-      if (d2 <= bound) {
-        const unsigned int idx = g.sidx ? (unsigned int)g.sidx[cs + j] : (unsigned int)(cs + j);
-        const unsigned long long k = ((unsigned long long)__float_as_uint(d2) << 32) | idx;
-        best = k < best ? k : best;
-      }
-    }
-    unsigned long long wb = best;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const unsigned long long t = __shfl_xor_sync(kAll, wb, o);
-      wb = t < wb ? t : wb;
-    }
-    best = wb;
-    if (wb != ~0ull) bound = fminf(bound, __uint_as_float((unsigned int)(wb >> 32)));
+    nn_sweep(g, cs, cc, qx, qy, qz, acc0, skipmask, lane, best, bidx, bound);
   }
   if (best == ~0ull) return -1;
   if (d2_out) *d2_out = __uint_as_float((unsigned int)(best >> 32));
-  return (int)(unsigned int)(best & 0xffffffffu);
+  if (key_out) *key_out = best;
+  return (int)bidx;
 }
 
 // Outer shell of the 5x5x5 block (cells with a coordinate offset of +-2): continues a search started by nn_search on
 // the inner 27 cells when the ball of the current bound sticks out of them.  `best` / `bound` are warp-uniform.
 __device__ void nn_search_shell(const PGrid &g, bool cursor_mode, int group, float qx, float qy, float qz, float acc0,
-                                unsigned int skipmask, int lane, unsigned long long &best, float &bound) {
+                                unsigned int skipmask, int lane, unsigned long long &best, unsigned int &bidx,
+                                float &bound) {
   const float ux = cell_u(qx, g.lo0, g.inv_cs), uy = cell_u(qy, g.lo1, g.inv_cs), uz = cell_u(qz, g.lo2, g.inv_cs);
   const float fx = floorf(ux), fy = floorf(uy), fz = floorf(uz);
   const int cx = clamp_cell((int)fx), cy = clamp_cell((int)fy), cz = clamp_cell((int)fz);
@@ -258,24 +281,7 @@ __device__ void nn_search_shell(const PGrid &g, bool cursor_mode, int group, flo
       const int src = __ffs(todo) - 1;
       todo &= todo - 1;
       const int cs = __shfl_sync(kAll, start, src), cc = __shfl_sync(kAll, count, src);
-      for (int j = lane; j < cc; j += 32) {
-        const float4 p = g.sorted[cs + j];
-        if (__float_as_uint(p.x) & skipmask) continue;
-        const float d2 = dist2_acc(acc0, p.y, p.z, p.w, qx, qy, qz);
-        if (d2 <= bound) {
-          const unsigned int idx2 = g.sidx ? (unsigned int)g.sidx[cs + j] : (unsigned int)(cs + j);
-          const unsigned long long k = ((unsigned long long)__float_as_uint(d2) << 32) | idx2;
-          best = k < best ? k : best;
-        }
-      }
-      unsigned long long wb = best;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long t = __shfl_xor_sync(kAll, wb, o);
-        wb = t < wb ? t : wb;
-      }
-      best = wb;
-      if (wb != ~0ull) bound = fminf(bound, __uint_as_float((unsigned int)(wb >> 32)));
+      nn_sweep(g, cs, cc, qx, qy, qz, acc0, skipmask, lane, best, bidx, bound);
     }
   }
 }
@@ -285,16 +291,18 @@ __device__ __forceinline__ int nn_search_rings(const PGrid &g, bool cursor_mode,
                                                float acc0, float r2, unsigned int skipmask, int lane, int rings,
                                                unsigned long long best0 = ~0ull) {
   float d2 = 0.f;
-  int r = nn_search(g, cursor_mode, group, qx, qy, qz, acc0, r2, skipmask, lane, &d2, best0);
+  unsigned long long best = ~0ull;
+  int r = nn_search(g, cursor_mode, group, qx, qy, qz, acc0, r2, skipmask, lane, &d2, best0, &best);
   if (rings < 2) return r;
   float bound = r >= 0 ? d2 : r2;
   // everything outside the inner block is farther than one cell (minus the fp32 slack of the cell coordinates)
   const float cover = 0.98f * g.cs;
   if (bound - acc0 <= cover * cover) return r;
-  unsigned long long best = r >= 0 ? (((unsigned long long)__float_as_uint(d2) << 32) | (unsigned int)r) : ~0ull;
-  nn_search_shell(g, cursor_mode, group, qx, qy, qz, acc0, skipmask, lane, best, bound);
+  unsigned int bidx = r >= 0 ? (unsigned int)r : 0xffffffffu;
+  if (r < 0) best = ~0ull;
+  nn_search_shell(g, cursor_mode, group, qx, qy, qz, acc0, skipmask, lane, best, bidx, bound);
   if (best == ~0ull) return -1;
-  return (int)(unsigned int)(best & 0xffffffffu);
+  return (int)bidx;
 }
 
 // One THREAD searches the inner 27 cells for the row nearest to the query with d2 <= bound.  Exact whenever the ball
@@ -318,6 +326,7 @@ __device__ unsigned long long nn_search_thread(const PGrid &g, bool cursor_mode,
     }
   }
   unsigned long long best = ~0ull;
+  unsigned int bidx = 0xffffffffu;
   for (int i = 0; i < 27; i++) {
     // own cell first (i = 0), then the others
     const int t = i == 0 ? 13 : (i <= 13 ? i - 1 : i);
@@ -337,15 +346,17 @@ __device__ unsigned long long nn_search_thread(const PGrid &g, bool cursor_mode,
       const float d2 = dist2_acc(acc0, p.y, p.z, p.w, qx, qy, qz);
       if (d2 <= bound) {
         const unsigned int idx = g.sidx ? (unsigned int)g.sidx[s + j] : (unsigned int)(s + j);
-        const unsigned long long k = ((unsigned long long)__float_as_uint(d2) << 32) | idx;
-        if (k < best) {
+        const unsigned long long k =
+            ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned int)(g.tie ? g.tie[idx] : (int)idx);
+        if (k < best || (k == best && idx < bidx)) {
           best = k;
+          bidx = idx;
           bound = d2;
         }
       }
     }
   }
-  return best;
+  return best == ~0ull ? ~0ull : ((best & 0xffffffff00000000ull) | bidx);
 }
 
 // upper_bound(off, n + 1 entries, x) - 1 : the segment that holds item x
@@ -1483,17 +1494,19 @@ trk_smooth_kernel(Trk A, int t, float w0, float w, int num_itr, float stopping) 
     const float bc1 = (float)(1.0 - b1t), bc2s = (float)sqrt(1.0 - b2t);
     for (int e = cth; e < S; e += cnth) {
       const int q = e & 1, fi = (e >> 1) % nf, c = (e >> 1) / nf, f = ra + fi;
-      const float vv = VEL(src, c, f, q);
+      // the neighbours' values were written by other CTAs of the cluster in the previous iteration: read them
+      // through L2 (ld.global.cg), never from a possibly stale L1 line
+      const float vv = __ldcg(&VEL(src, c, f, q));
       const float r = vv - VEL(A.diffs, c, f, q);
       float grad = w0 * 2.f * r / n1;
       double l = (double)w0 * r * r / n1;
       if (f < rb) {
-        const float d = vv - VEL(src, c, f + 1, q);
+        const float d = vv - __ldcg(&VEL(src, c, f + 1, q));
         grad += w * ((d > 0.f) - (d < 0.f)) / n2;
         l += (double)w * fabsf(d) / n2;
       }
       if (f > ra) {
-        const float d = VEL(src, c, f - 1, q) - vv;
+        const float d = __ldcg(&VEL(src, c, f - 1, q)) - vv;
         grad -= w * ((d > 0.f) - (d < 0.f)) / n2;
       }
       lsum += l;
@@ -1540,7 +1553,7 @@ trk_smooth_kernel(Trk A, int t, float w0, float w, int num_itr, float stopping) 
     const int q = e % 3, f = (e / 3) % kRelFrames, c = e / (3 * kRelFrames);
     const bool optimised = q < 2 && f >= ra && f <= rb;
     if (optimised) {
-      if (src != A.velos) VEL(A.velos, c, f, q) = VEL(src, c, f, q);
+      if (src != A.velos) VEL(A.velos, c, f, q) = __ldcg(&VEL(src, c, f, q));
     } else {
       VEL(A.velos, c, f, q) *= dec;
     }
@@ -1710,6 +1723,7 @@ PGrid make_pgrid(void *table, int64_t H, void *sorted, void *sidx, void *cells, 
   g.sidx = (int *)sidx;
   g.cells = (int *)cells;
   g.ctr = (int *)ctr;
+  g.tie = nullptr;
   g.lo0 = (float)lo[0];
   g.lo1 = (float)lo[1];
   g.lo2 = (float)lo[2];
@@ -1764,6 +1778,7 @@ IcpB make_icp(const pcs_trk_icp_t *P) {
   A.g_inst = (const int *)P->g_inst;
   A.ref = make_pgrid(P->ref_table, P->ref_H, P->ref_pts, nullptr, nullptr, nullptr, P->lo, P->cs);
   A.mov = make_pgrid(P->mov_table, P->mov_H, P->mov_sorted, P->mov_sidx, P->mov_cells, P->mov_ctr, P->lo, P->cs);
+  A.mov.tie = (const int *)P->mv_gid;
   A.mv = (float4 *)P->mv;
   A.mv_gid = (const int *)P->mv_gid;
   A.mv_inst = (const int *)P->mv_inst;

@@ -354,21 +354,24 @@ def cluster_labels(fxyz, radius, max_num_neighbors=32, chunk=10, num_frames=None
     return labels, n_comp
 
 
-def voxelize(points, grid_size, ignore_dim0=False, want_mean=True, want_max=False, want_counts=False):
+def voxelize(points, grid_size, ignore_dim0=False, want_mean=True, want_max=False, want_counts=False,
+             want_sums=False, bounds_hook=None):
     """GridSampling3D.forward on the device (grid_sampling.py:22-46).
 
     points f32[N,4]; grid_size [gx,gy,gz] (the frame digit has size 1).  Voxels are numbered by ascending
     cell key (torch.unique(sorted=True)).  Returns a dict with `inv` int64[N], `num` (python int, one host
     sync) and optionally `sampled` f32[V,4] (mean of all columns), `maxidx` int64[V] (highest point index
     per voxel: simple_reg.py:122-124), `counts` int32[V].  ignore_dim0 treats column 0 as zero
-    (preprocessor_utils.grid_sample :21-30).
+    (preprocessor_utils.grid_sample :21-30).  want_sums adds the fp64 per-voxel column sums f64[V,4];
+    bounds_hook(bounds) may widen the point bounds in place before the grid is derived (frame-window sharding:
+    all ranks voxelize on the grid of the whole sequence).
     """
     pts = _as_points(points, "points")
     n, dev = pts.shape[0], pts.device
     L = _lib.lib()
     size = [1.0] + [float(np.float32(g)) for g in grid_size]
     out = {}
-    if n == 0:
+    if n == 0 and bounds_hook is None:
         out.update(inv=torch.zeros(0, dtype=torch.int64, device=dev), num=0)
         return out
     with torch.cuda.device(dev):
@@ -376,6 +379,8 @@ def voxelize(points, grid_size, ignore_dim0=False, want_mean=True, want_max=Fals
         bounds = torch.empty(8, dtype=torch.int32, device=dev)
         _lib.check(L.pcs_bounds_init(s, _ptr(bounds), 1), "pcs_bounds_init")
         _lib.check(L.pcs_bounds_update(s, _ptr(pts), n, 1, 1, _ptr(bounds)), "pcs_bounds_update")
+        if bounds_hook is not None:
+            bounds_hook(bounds)
         start = torch.empty(4, dtype=torch.float32, device=dev)
         strides = torch.empty(5, dtype=torch.int64, device=dev)
         _lib.check(L.pcs_voxelize_params(s, _ptr(bounds), _f4(size), int(ignore_dim0), _ptr(start), _ptr(strides)),
@@ -384,7 +389,7 @@ def voxelize(points, grid_size, ignore_dim0=False, want_mean=True, want_max=Fals
         table = torch.empty(H, 4, dtype=torch.int32, device=dev)
         pt_vid = torch.empty(n, dtype=torch.int32, device=dev)
         # per-voxel rows are indexed by dense id: n rows allocated, the first V touched
-        sums = torch.empty(n, 4, dtype=torch.float64, device=dev) if want_mean else None
+        sums = torch.empty(n, 4, dtype=torch.float64, device=dev) if (want_mean or want_sums) else None
         maxidx = torch.empty(n, dtype=torch.int32, device=dev) if want_max else None
         cnt = torch.empty(n, dtype=torch.int32, device=dev)
         ukeys = torch.empty(n, dtype=torch.int64, device=dev)
@@ -405,14 +410,16 @@ def voxelize(points, grid_size, ignore_dim0=False, want_mean=True, want_max=Fals
                                     tb), "pcs_sort_pairs")
         inv = torch.empty(n, dtype=torch.int64, device=dev)
         rank_of = torch.empty(max(V, 1), dtype=torch.int32, device=dev)
-        sampled = torch.empty(V, 4, dtype=torch.float32, device=dev) if want_mean else None
+        sampled = torch.empty(V, 4, dtype=torch.float32, device=dev) if (want_mean or want_sums) else None
         maxidx_out = torch.empty(V, dtype=torch.int64, device=dev) if want_max else None
         counts = torch.empty(V, dtype=torch.int32, device=dev) if want_counts else None
         _lib.check(L.pcs_voxelize_finish(s, _ptr(ids_sorted), V, _ptr(pt_vid), n, _ptr(sums), _ptr(maxidx), _ptr(cnt),
                                          _ptr(rank_of), _ptr(inv), _ptr(sampled), _ptr(maxidx_out), _ptr(counts)),
                    "pcs_voxelize_finish")
     out.update(inv=inv, num=V, keys=keys_sorted)
-    if want_mean:
+    if want_sums:
+        out["sums"] = sums[ids_sorted.long()]
+    if want_mean or want_sums:
         out["sampled"] = sampled
     if want_max:
         out["maxidx"] = maxidx_out

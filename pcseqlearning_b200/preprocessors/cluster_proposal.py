@@ -7,7 +7,7 @@ same as the reference's per-chunk calls."""
 import torch
 from torch import nn
 
-from .. import graph_utils, ops
+from .. import graph_utils, ops, parallel
 from ..utils import EasyDict, Timer
 from .eval_utils import FrameBoxes
 
@@ -29,7 +29,9 @@ class ClusterProposal(nn.Module):
     def propose_cluster(self, seq_dict):
         """point_fxyz [N,4] (after ground removal) -> seq_dict['point_<comp_key>'] int64[N]."""
         fxyz = seq_dict["point_fxyz"]
-        num_frames = int(seq_dict["point_sweep"].max().long().item()) + 1
+        shard = parallel.SHARD
+        num_frames = shard.F if shard is not None else int(seq_dict["point_sweep"].max().long().item()) + 1
+        seq_dict["num_frames"] = num_frames
         verbose = self.model_cfg.get("VERBOSE", True)
         graphs = [getattr(self, f"graph_{k}") for k in self.component_keys]
         same_k = len({int(g.max_num_neighbors) for g in graphs}) == 1
@@ -40,17 +42,31 @@ class ClusterProposal(nn.Module):
                                                           int(graphs[0].max_num_neighbors), chunk=CHUNK_FRAMES,
                                                           num_frames=num_frames)
             for comp_key, lab, nc in zip(self.component_keys, labels, n_comp):
-                seq_dict[f"point_{comp_key}"] = lab
-                seq_dict[f"num_{comp_key}"] = nc
+                seq_dict[f"point_{comp_key}"], seq_dict[f"num_{comp_key}"] = self._globalize(lab, nc, fxyz)
             return seq_dict
         for comp_key in self.component_keys:
             with Timer(f"Propose Cluster for {comp_key}", verbose=verbose):
                 graph = getattr(self, f"graph_{comp_key}")
                 labels, n_comp = ops.cluster_labels(fxyz, float(graph.radius), int(graph.max_num_neighbors),
                                                     chunk=CHUNK_FRAMES, num_frames=num_frames)
-                seq_dict[f"point_{comp_key}"] = labels
-                seq_dict[f"num_{comp_key}"] = n_comp
+                seq_dict[f"point_{comp_key}"], seq_dict[f"num_{comp_key}"] = self._globalize(labels, n_comp, fxyz)
         return seq_dict
+
+    @staticmethod
+    def _globalize(labels, n_comp, fxyz):
+        """Frame-window sharding: this rank numbered the components of ITS chunks with a running offset; the
+        per-chunk counts of all ranks (disjoint chunks: sum == gather) give the sequence-wide running offset of
+        cluster_proposal.py:80-81."""
+        shard = parallel.SHARD
+        if shard is None:
+            return labels, n_comp
+        counts = shard.all_reduce_sum(n_comp.clone())
+        chunk = torch.div(fxyz[:, 0].round().long(), CHUNK_FRAMES, rounding_mode="floor")
+        local_off = torch.cumsum(n_comp, 0) - n_comp
+        global_off = torch.cumsum(counts, 0) - counts
+        if labels.numel():
+            labels = labels - local_off[chunk] + global_off[chunk]
+        return labels, counts
 
     # ---- GT bookkeeping (evaluation, cluster_proposal.py:90-285) --------------------------------------------
     def format_boxes(self, seq_dict, num_frames):
@@ -118,8 +134,12 @@ class ClusterProposal(nn.Module):
             after[fb.order] = best_sorted.to(best_iou)
             seq_boxes[f"best_iou_after_{comp_key}"] = after
         best_iou[fb.order] = best_sorted.to(best_iou)
+        trace_best = trace_best64.to(trace_best)
+        if parallel.SHARD is not None:  # every rank evaluated its own frames
+            parallel.SHARD.all_reduce_max(best_iou)
+            parallel.SHARD.all_reduce_max(trace_best)
         seq_dict["gt_box_best_iou"] = best_iou
-        seq_dict["gt_trace_best_iou"] = trace_best64.to(trace_best)
+        seq_dict["gt_trace_best_iou"] = trace_best
         seq_dict["point_gt_box_id"] = gt_local.to(comps[-1])
         seq_dict["point_gt_trace_id"] = gt_trace.to(comps[-1])
         seq_dict["point_pred_trace_id"] = pred_trace

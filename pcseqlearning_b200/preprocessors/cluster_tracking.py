@@ -11,7 +11,7 @@ import numpy as np
 import torch
 from torch import nn
 
-from .. import _lib, graph_utils, ops
+from .. import _lib, graph_utils, ops, parallel
 from ..grid_sampling import GridSampling3D
 from ..utils import EasyDict, Timer, filter_dict
 from ..utils.scatter import scatter_max, scatter_min
@@ -524,7 +524,8 @@ class ClusterTracking(nn.Module):
             if key in seq_dict:
                 all_points[key] = seq_dict[key]
         all_points = EasyDict(filter_dict(all_points, seq_dict["full_point_height"] > 0.0))
-        num_frames = int(seq_points.frame.max().long().item()) + 1
+        shard = parallel.SHARD
+        num_frames = shard.F if shard is not None else int(seq_points.frame.max().long().item()) + 1
         sequence_id = seq_dict["frame_id"][0][:-4]
         outfolder = f"{self.model_cfg.DIR}/{sequence_id}"
         outpath = f"{outfolder}/all.pth"
@@ -551,7 +552,34 @@ class ClusterTracking(nn.Module):
 
             mark("start")
             comps = [seq_dict[f"point_{k}"] for k in self.component_keys]
-            tb = TrackBatch(seq_points.fxyz, seq_points.frame, comps, self.model_cfg, num_frames=num_frames)
+            anchors = None
+            if shard is not None:
+                # halo exchange (NCCL all-to-all over NVLink): every rank receives the frames
+                # [first anchor - interval, last anchor + interval] of its block of tracking anchors
+                pack = dict(fxyz=seq_points.fxyz)
+                for i, c in enumerate(comps):
+                    pack[f"c{i}"] = c
+                for key in ["instance_label", "segmentation_label"]:
+                    if key in seq_points:
+                        pack[key] = seq_points[key]
+                got, fr = shard.exchange_frames(pack, seq_points.frame.reshape(-1))
+                seq_points = EasyDict(fxyz=got["fxyz"], frame=fr.reshape(-1, 1).to(seq_points.frame.dtype))
+                for key in ["instance_label", "segmentation_label"]:
+                    if key in got:
+                        seq_points[key] = got[key]
+                comps = [got[f"c{i}"] for i in range(len(comps))]
+                apack = {k: v for k, v in all_points.items() if k != "frame"}
+                agot, afr = shard.exchange_frames(apack, all_points.frame.reshape(-1))
+                all_points = EasyDict(agot)
+                all_points["frame"] = afr.reshape(-1, 1).to(seq_dict["full_point_sweep"].dtype)
+                anchors = list(shard.anchors)
+                mark("halo")
+            if anchors is not None and (len(anchors) == 0 or seq_points.fxyz.shape[0] == 0):
+                seq_dict["tracking_results"], seq_dict["tracking_boxes"] = {}, seq_boxes
+                shard.all_reduce_max(seq_boxes.best_iou)
+                return seq_dict
+            tb = TrackBatch(seq_points.fxyz, seq_points.frame, comps, self.model_cfg, num_frames=num_frames,
+                            anchors=anchors)
             mark("setup")
             tb.run()
             mark("run")
@@ -572,6 +600,16 @@ class ClusterTracking(nn.Module):
                         torch.save(extracted, f"{outfolder}/{frame_id:03d}_{comp_key}.pth")
                     results[f"{frame_id:03d}_{comp_key}"] = extracted
             seq_dict["tracking_batch"] = tb
+            if shard is not None:
+                # every rank updated the boxes of the frames its anchors reach; max-merge like the reference's
+                # sequential `if iou > best_iou` updates (:410-414).  Track ids (anchor frame, key, local component)
+                # are globally unique, so merging them is a gather of the per-instance index.
+                shard.all_reduce_max(seq_boxes.best_iou)
+                idx = torch.tensor([[tb.inst_anchor_h[j], tb.inst_key_h[j], shard.rank,
+                                     int(results[f"{tb.inst_anchor_h[j]:03d}_{self.component_keys[tb.inst_key_h[j]]}"]
+                                         ["fxyz"].shape[0])] for j in range(tb.J)], dtype=torch.int64,
+                                   device=seq_boxes.best_iou.device).reshape(-1, 4)
+                seq_dict["tracking_index"], _ = shard.all_gather_v(idx)
             mark("assemble")
             if timing:
                 names = ["count", "ranges", "scatter", "search", "solve", "stop", "final", "ratio"]

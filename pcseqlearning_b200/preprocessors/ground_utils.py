@@ -11,15 +11,32 @@ torch programs on a few thousand cells (SURVEY.md section 8f ranks moving them i
 import numpy as np
 import torch
 
-from .. import _lib, ops
+from .. import _lib, ops, parallel
 from ..utils import EasyDict
 from ..utils.scatter import scatter_count, scatter_max, scatter_mean, scatter_min, scatter_sum
 
 
 def grid_sample(point_fxyz, grid_size):
-    """Voxel means with the frame column zeroed + point->voxel map (preprocessor_utils.py:21-30)."""
-    res = ops.voxelize(point_fxyz, grid_size, ignore_dim0=True, want_mean=True)
-    return EasyDict(bxyz=res["sampled"]), res["inv"]
+    """Voxel means with the frame column zeroed + point->voxel map (preprocessor_utils.py:21-30).
+
+    Frame-window sharding: the de-duplication ignores time, so the voxels are sequence-global.  Every rank voxelizes
+    its own frames on the grid of the whole sequence, the partial (column sums, count) per cell are all-gathered and
+    merged by cell key; all ranks end up with the identical, ascending-key voxel list of a single-GPU run."""
+    shard = parallel.SHARD
+    if shard is None:
+        res = ops.voxelize(point_fxyz, grid_size, ignore_dim0=True, want_mean=True)
+        return EasyDict(bxyz=res["sampled"]), res["inv"]
+    res = ops.voxelize(point_fxyz, grid_size, ignore_dim0=True, want_sums=True, want_counts=True,
+                       bounds_hook=shard.reduce_bounds)
+    keys, _ = shard.all_gather_v(res["keys"])
+    sums, _ = shard.all_gather_v(res["sums"])
+    cnts, _ = shard.all_gather_v(res["counts"].long())
+    uk, inv = torch.unique(keys, return_inverse=True)
+    gs = torch.zeros(uk.shape[0], 4, dtype=torch.float64, device=keys.device).index_add_(0, inv, sums)
+    gc = torch.zeros(uk.shape[0], dtype=torch.int64, device=keys.device).index_add_(0, inv, cnts)
+    bxyz = (gs / gc.clamp(min=1)[:, None].double()).float()
+    point_voxel = torch.searchsorted(uk, res["keys"][res["inv"]])
+    return EasyDict(bxyz=bxyz), point_voxel
 
 
 def format_pillars(points, pillar_size, pc_range_min):
@@ -103,7 +120,23 @@ def compute_min_height_from_ransac(pillar_dims, num_pillars, voxels, pillars, cf
     best_normal[:, -1] = 1.0
     best_center = c_min_z.new_zeros(num_coarse, 3)
     ratios = torch.linspace(0.3, 1, 30)
-    if use_kernels:
+    shard = parallel.SHARD
+    if use_kernels and shard is not None and shard.world > 1:
+        # the 30 height ratios are independent IRLS problems: every rank solves a contiguous slice of them and the
+        # per-super-pillar winners are merged in ratio order with the reference's strict '<' (first maximum wins)
+        r0, r1 = (30 * shard.rank) // shard.world, (30 * (shard.rank + 1)) // shard.world
+        vox_sorted = ops.gather_rows(voxels.bxyz, order)
+        if r1 > r0:
+            bc, bn, bf, _ = ops.ground_ransac(vox_sorted, cidx, num_coarse, c_min_z, c_max_z, ratios[r0:r1], cfg.SIGMA2)
+        else:
+            bc, bn, bf = best_center, best_normal, best_conf
+        packed = torch.cat([bc, bn, bf[:, None]], 1).contiguous()
+        for part in shard.all_gather(packed):
+            better = best_conf < part[:, 6]
+            best_normal = torch.where(better[:, None], part[:, 3:6], best_normal)
+            best_center = torch.where(better[:, None], part[:, :3], best_center)
+            best_conf = torch.where(better, part[:, 6], best_conf)
+    elif use_kernels:
         # all 30 x <=50 IRLS iterations inside one persistent cooperative launch
         best_center, best_normal, best_conf, _ = ops.ground_ransac(ops.gather_rows(voxels.bxyz, order), cidx, num_coarse, c_min_z,
                                                                    c_max_z, ratios, cfg.SIGMA2)
@@ -215,7 +248,10 @@ def ground_plane_removal(point_fxyz, cfg, warmup=None, use_kernels=True):
     Returns (height [N], horizon [N] bool, fitting_error [N], pillar_height [X,Y], pillar_min_z [X,Y]).
     """
     pillar_size = torch.tensor(cfg.PILLAR_SIZE).to(point_fxyz)
-    pc_range_min = point_fxyz[:, 1:3].min(0)[0] - 0.05
+    pc_range_min = point_fxyz[:, 1:3].min(0)[0] if point_fxyz.shape[0] else point_fxyz.new_full((2,), 1e30)
+    if parallel.SHARD is not None:
+        pc_range_min = -parallel.SHARD.all_reduce_max(-pc_range_min)
+    pc_range_min = pc_range_min - 0.05
     voxels, point_voxel_index = grid_sample(point_fxyz, [0.10, 0.10, 0.03])
     pillar_dims, num_pillars, voxels, pillars = format_pillars(voxels, pillar_size, pc_range_min)
     if warmup is not None:

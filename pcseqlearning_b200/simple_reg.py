@@ -8,7 +8,7 @@ import numpy as np
 import torch
 from torch import nn
 
-from . import ops
+from . import ops, parallel
 from . import preprocessors as preprocessor
 from .utils import EasyDict, filter_dict
 
@@ -91,7 +91,10 @@ class SimpleReg(RegistrationTemplate):
         """Flatten the per-frame GT boxes, drop empty slots, derive track labels and per-box speed
         (simple_reg.py:35-101)."""
         sweep = seq_dict["point_sweep"]
-        num_frames = int(sweep.max().long().item()) - int(sweep.min().long().item()) + 1
+        if parallel.SHARD is not None:  # frame-window sharding: the GT arrays cover the whole sequence
+            num_frames = parallel.SHARD.F
+        else:
+            num_frames = int(sweep.max().long().item()) - int(sweep.min().long().item()) + 1
         attr = seq_dict["gt_box_attr"].reshape(-1, 7)
         cls_label = seq_dict["gt_box_cls_label"].reshape(-1)
         assert attr.shape[0] % num_frames == 0, "gt boxes must be padded to a fixed count per frame"
@@ -151,7 +154,9 @@ class SimpleReg(RegistrationTemplate):
             seq_dict.pop("point_bxyz")
             if self.subsample:
                 # one (highest-index) point per 0.08 m cell, arrays re-ordered by ascending cell key
-                res = ops.voxelize(seq_dict["point_fxyz"], self.subsample_grid, want_mean=False, want_max=True)
+                hook = parallel.SHARD.reduce_bounds if parallel.SHARD is not None else None
+                res = ops.voxelize(seq_dict["point_fxyz"], self.subsample_grid, want_mean=False, want_max=True,
+                                   bounds_hook=hook)
                 pick = res["maxidx"]
                 for key in ["point_fxyz", "point_feat", "segmentation_label", "instance_label", "is_foreground",
                             "point_sweep"]:

@@ -307,7 +307,13 @@ class TrackBatch:
                 keys = _e(Vc, torch.int64, dev)
                 _lib.check(L.pcs_trk_cell_keys(s, _ptr(cat_pts), _ptr(cat_grp.int().contiguous()), Vc, lo_c, cs,
                                                _ptr(keys)), "pcs_trk_cell_keys")
-                ks, perm = torch.sort(keys)
+                # canonical row order (cell key, then x, y, z): equal-distance ties of the searches are resolved by row,
+                # and the sampler emits voxels in a run-dependent order
+                perm = torch.arange(Vc, device=dev)
+                for col in (3, 2, 1):
+                    perm = perm[torch.sort(cat_pts[perm, col], stable=True)[1]]
+                ks, o2 = torch.sort(keys[perm], stable=True)
+                perm = perm[o2]
                 rv = cat_pts[perm].contiguous()
                 rv_grp = cat_grp[perm]
                 uk, cnt = torch.unique_consecutive(ks, return_counts=True)
