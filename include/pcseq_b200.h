@@ -365,6 +365,61 @@ int pcs_points_in_boxes(pcs_stream_t s, const float *pts, const int32_t *sel, in
                         const int64_t *cid2, int32_t *cnt0, int32_t *cnt1, int32_t *cnt2, int32_t *first_out,
                         int32_t *err);
 
+
+/* ---- reference torch_hash op on caller-supplied voxel coordinates -------------------------------------
+ * The four entry points of pcdet/ops/torch_hash (torch_hash.h:16-32, torch_hash_api.cpp:9-15) for callers that bring
+ * their own integer voxel coordinates (HashTable.find_corres*, torch_hash_modules.RadiusGraph / ChamferDistance).
+ * key = map2key(coord, dims) with the reference's clamp; cells [coord + qmin, coord + qmax] (dimension 0 fastest);
+ * fp32 distance over all nd <= 4 columns with one FMA per dimension.  The table holds one 16-byte slot per occupied
+ * cell (H power of two, >= 2 n is always enough) and `rows` the point indices grouped by cell -- the caller's
+ * (keys, values, reverse_indices) buffers of the reference signatures are opaque scratch for the binding
+ * (pcseqlearning_b200/torch_hash_cuda.py).  dims / qmin / qmax are HOST arrays.
+ *   pcs_compat_hash_insert     hash_insert_gpu      (torch_hash_kernel.cu:54-91, 411-442)
+ *   pcs_compat_radius_degree   first pass of radius_graph_gpu (:224-288); K = -1 counts all neighbours
+ *   pcs_compat_radius_fill     second pass (:290-409): edges int64[E][2] rows (ref, query), ascending query, ascending
+ *                              (distance, index) inside a query; offsets = exclusive scan of degree
+ *   pcs_nn_correspondence      correspondence       (:96-155): nearest row, NO radius test, -1 if no cell is occupied
+ *   pcs_points_in_radius       points_in_radius_gpu (:160-222): visited[row] = 1 for d2 < r*r (strict) */
+int pcs_compat_hash_insert(pcs_stream_t s, const int64_t *coords, int64_t n, int nd, const int64_t *dims_host,
+                           pcs_slot_t *table, int64_t H, int32_t *rows, int32_t *ctr);
+int pcs_compat_radius_degree(pcs_stream_t s, const pcs_slot_t *table, int64_t H, const int32_t *rows,
+                             const float *values, int nd, const int64_t *dims_host, const int64_t *qcoords,
+                             const float *qvalues, int64_t m, const int *qmin, const int *qmax, const float *radius,
+                             int K, int32_t *degree);
+int pcs_compat_radius_fill(pcs_stream_t s, const pcs_slot_t *table, int64_t H, const int32_t *rows, const float *values,
+                           int nd, const int64_t *dims_host, const int64_t *qcoords, const float *qvalues, int64_t m,
+                           const int *qmin, const int *qmax, const float *radius, const int32_t *degree,
+                           const int64_t *offsets, int64_t *edges, float *dists);
+int pcs_nn_correspondence(pcs_stream_t s, const pcs_slot_t *table, int64_t H, const int32_t *rows, const float *values,
+                          int nd, const int64_t *dims_host, const int64_t *qcoords, const float *qvalues, int64_t m,
+                          const int *qmin, const int *qmax, int64_t *corres);
+int pcs_points_in_radius(pcs_stream_t s, const pcs_slot_t *table, int64_t H, const int32_t *rows, const float *values,
+                         int nd, const int64_t *dims_host, const int64_t *qcoords, const float *qvalues, int64_t m,
+                         const int *qmin, const int *qmax, float radius, int64_t *visited);
+
+
+/* ---- composite entry points (the names of SURVEY.md section 8b) -----------------------------------------
+ * pcs_radius_graph          = pcs_radius_search (single pass, multi-radius capable)
+ * pcs_connected_components  = pcs_uf_init + pcs_uf_union_edges + pcs_uf_labels (graph_utils.py:40-53)
+ * pcs_voxelize              = pcs_voxelize_params + _insert + pcs_sort_pairs + _finish (grid_sampling.py:22-46);
+ *                             synchronises the stream once, *num_voxels (host) receives V
+ * pcs_register_icp          = pcs_trk_icp (registration_utils.py:83-206 for a batch of instances) */
+int pcs_radius_graph(pcs_stream_t s, const pcs_slot_t *table, int64_t H, const float *sorted_pts,
+                     const int32_t *sorted_idx, int seg_div, int n_seg, const float *seg_lo, const int64_t *seg_dims,
+                     const float *vs, const float *queries, int64_t m, const int32_t *order, const int *qmin,
+                     const int *qmax, const float *radius, float radius_scalar, int K, int32_t *nbr_idx, float *nbr_d2,
+                     int32_t *nbr_cnt, int32_t *const *uf_parents, const float *uf_r2, const int *uf_need_full, int n_uf,
+                     const int32_t *skip_full_cnt, const uint32_t *occ, int64_t occ_bits);
+int pcs_connected_components(pcs_stream_t s, int32_t *parent, const int64_t *e0, const int64_t *e1, int64_t E, int64_t n,
+                             const int32_t *seg_of, int n_seg, int64_t *labels, int64_t *n_comp, void *tmp,
+                             int64_t tmp_bytes);
+int pcs_voxelize(pcs_stream_t s, const float *pts, int64_t n, const uint32_t *bounds, const float *size, int ignore_dim0,
+                 float *start, int64_t *strides, void *table, int64_t H, int32_t *pt_vid, double *sums, int32_t *maxidx,
+                 int32_t *counts, int64_t *ukeys, int32_t *uids, int32_t *counters, int64_t *keys_sorted,
+                 int32_t *ids_sorted, void *sort_tmp, int64_t sort_tmp_bytes, int32_t *rank_of, int64_t *inv,
+                 float *sampled, int64_t *maxidx_out, int32_t *counts_out, int64_t *num_voxels);
+int pcs_register_icp(pcs_stream_t s, const pcs_trk_icp_t *P);
+
 #ifdef __cplusplus
 }
 #endif

@@ -83,6 +83,27 @@ _SIGNATURES = {
                                    c_void_p, c_void_p, c_void_p, c_void_p]),
     "pcs_trk_group_nn": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_double, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p]),
+    "pcs_compat_hash_insert": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64, c_void_p,
+                                       c_void_p]),
+    "pcs_compat_radius_degree": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                                         c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "pcs_compat_radius_fill": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                                       c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_void_p]),
+    "pcs_nn_correspondence": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                                      c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "pcs_points_in_radius": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                                     c_void_p, c_int64, c_void_p, c_void_p, c_float, c_void_p]),
+    "pcs_radius_graph": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
+                                 c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
+                                 c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                 c_void_p, c_void_p, c_int64]),
+    "pcs_connected_components": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int,
+                                         c_void_p, c_void_p, c_void_p, c_int64]),
+    "pcs_voxelize": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                             c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                             c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pcs_register_icp": (c_int, [c_void_p, c_void_p]),
     "pcs_box_prep": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "pcs_points_in_boxes": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int,
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

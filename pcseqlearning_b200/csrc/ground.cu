@@ -9,6 +9,8 @@
 // Both loops run to completion inside ONE launch with their stopping rules evaluated on the device.
 #include <cooperative_groups.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
@@ -389,7 +391,8 @@ constexpr int kMaxRansacGrid = 2048;
 __device__ unsigned int g_bal_dur[kMaxRansacGrid];
 __device__ long long g_bal_v0[kMaxRansacGrid];
 
-__global__ void __launch_bounds__(kRansacThreads, 3) ground_ransac_kernel(RansacArgs A) {
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kRansacThreads, kMinBlocks) ground_ransac_kernel(RansacArgs A) {
   cg::grid_group grid = cg::this_grid();
   __shared__ __align__(16) float s_new[kG][kGroup][8];
   __shared__ __align__(16) float s_old[kG][kGroup][8];
@@ -782,9 +785,18 @@ int pcs_ground_ransac(pcs_stream_t s, const float *vox, const int32_t *cidx, con
   int dev = 0, sms = 148, per_sm = 1;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ground_ransac_kernel, kRansacThreads, 0);
+  // 3 CTAs / SM at 80 registers (616 B of spills, all in the per-iteration plane-fit phase) or 2 CTAs / SM with 128
+  // registers and no spills (PCS_RANSAC_OCC=2).  Measured on B200, 198 frames: 37.4 ms vs 41.1 ms -- the voxel sweep
+  // is latency bound and the third resident CTA is worth more than the spills cost, so 3 stays the default.
+  static int occ = -1;
+  if (occ < 0) {
+    const char *o = getenv("PCS_RANSAC_OCC");
+    occ = (o && atoi(o) == 2) ? 2 : 3;
+  }
+  const void *kern = occ == 3 ? (const void *)ground_ransac_kernel<3> : (const void *)ground_ransac_kernel<2>;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kRansacThreads, 0);
   if (per_sm < 1) per_sm = 1;
-  if (per_sm > 3) per_sm = 3;
+  if (per_sm > occ) per_sm = occ;
   const int n_teams = (n_ratios + kG - 1) / kG;
   long long bpt = (Nv + 4095) / 4096;  // at least ~4k voxels per block
   long long cap = ((long long)sms * per_sm) / n_teams;
@@ -794,7 +806,7 @@ int pcs_ground_ransac(pcs_stream_t s, const float *vox, const int32_t *cidx, con
   if (blocks < n_ratios) blocks = n_ratios;  // the in-kernel team assignment needs one block per active ratio
   if (blocks > kMaxRansacGrid) blocks = kMaxRansacGrid;
   void *args[] = {&A};
-  cudaError_t e = cudaLaunchCooperativeKernel((void *)ground_ransac_kernel, dim3((unsigned)blocks),
+  cudaError_t e = cudaLaunchCooperativeKernel(kern, dim3((unsigned)blocks),
                                               dim3(kRansacThreads), args, 0, as_stream(s));
   g_launches++;
   if (e != cudaSuccess) return set_error((int)e, "ground_ransac_kernel (cooperative launch)");

@@ -241,7 +241,11 @@ radius_search_kernel(const pcs_slot_t *__restrict__ table, long long mask, const
     if (nbr_cnt && lane == 0) nbr_cnt[q] = cnt;
     if (kFusedUF) {
       const float my_d2 = __uint_as_float((unsigned int)(best >> 32));
-      for (int k = 0; k < uf.n; k++) {
+      // fully unrolled over the (at most 3) forests: a runtime index into the by-value UfTargets arrays would put
+      // the struct into local memory (LDL / STL in the hot loop)
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        if (k >= uf.n) break;
         if (uf.need_full[k] && cnt < K) continue;
         // hook the roots of the query and of its neighbours within r2[k] under the smallest of them
         int *parent = uf.parent[k];

@@ -1,11 +1,10 @@
 """Module-style API of the reference's torch_hash op (mirror of pcdet/ops/torch_hash/torch_hash_modules.py:10-126)
 on the new kernels: ``RadiusGraph(max_num_points, ndim)`` and ``ChamferDistance``.
 
-The four raw functions of ``torch_hash_cuda`` that operate on caller-allocated multimap buffers
-(``hash_insert_gpu`` / ``radius_graph_gpu`` / ``correspondence`` / ``points_in_radius_gpu``,
-torch_hash_api.cpp:9-15) are not re-exported: the table layout behind them is gone (unique-cell table + cell-sorted
-points); their only caller on the cluster-tracking path, ``graph_utils.RadiusGraph``, is served by
-``pcseqlearning_b200.graph_utils``.  ``correspondence`` / ``points_in_radius`` are provided as functions on points.
+The four raw functions of the native module (``hash_insert_gpu`` / ``radius_graph_gpu`` / ``correspondence`` /
+``points_in_radius_gpu``, torch_hash_api.cpp:9-15) live in ``pcseqlearning_b200.torch_hash_cuda`` with the reference's
+signatures; ``correspondence`` / ``points_in_radius`` below are the point-level conveniences of
+``HashTable.find_corres`` / ``points_in_radius_step2`` (torch_hash_utils.py:32-75, 116-150) on top of them.
 """
 import torch
 from torch import nn
@@ -56,14 +55,46 @@ class ChamferDistance(nn.Module):
         return dist_fwd + dist_bwd
 
 
-def correspondence(ref, query, radius):
-    """Nearest reference point of every query within the 27 cells of size `radius` (-1 when the cells are empty);
-    the reference's `correspondence` (torch_hash_kernel.cu:96-155) has no radius test, so pass the cell size and
-    accept matches up to the cell diagonal."""
-    ref_p = ops._as_points(ref)
-    query_p = ops._as_points(query)
-    grid = ops.CellGrid(ref_p, ops.radius_voxel_size(radius), bounds_sets=[ref_p, query_p])
-    idx, cnt, _ = grid.search(query_p, 1, float(radius) * 3.5)
-    out = idx[:, 0].long()
-    out[cnt == 0] = -1
+def _voxelization(ref_p, query_p, voxel_size):
+    """graph_utils.py:170-176 geometry: coordinates of both sets and dims for a [1 - 1e-3, v, v, v] grid."""
+    vs = torch.tensor(ops.radius_voxel_size(voxel_size), device=ref_p.device)
+    allp = torch.cat([ref_p, query_p], 0)
+    lo = allp.min(0)[0] - vs * 2
+    hi = allp.max(0)[0] + vs * 2
+    coord = lambda x: torch.round((x - lo) / vs).long() + 1
+    return coord(ref_p), coord(query_p), torch.round((hi - lo) / vs).long() + 3
+
+
+def _table(ref_p, coords, dims):
+    from . import torch_hash_cuda as op
+    H = max(int(ref_p.shape[0] / 0.5), 8)
+    keys = torch.full((H,), -1, dtype=torch.int64, device=ref_p.device)
+    values = torch.empty(H, 4, dtype=torch.float32, device=ref_p.device)
+    rev = torch.zeros(H, dtype=torch.int64, device=ref_p.device)
+    op.hash_insert_gpu(keys, values, rev, dims, coords, ref_p)
+    return keys, values, rev
+
+
+def correspondence(ref, query, voxel_size):
+    """Nearest reference point of every query over the 27 cells (size `voxel_size`) around it, with NO radius test
+    (torch_hash_kernel.cu:96-155): -1 only when all 27 cells are empty."""
+    from . import torch_hash_cuda as op
+    ref_p, query_p = ops._as_points(ref), ops._as_points(query)
+    cr, cq, dims = _voxelization(ref_p, query_p, voxel_size)
+    keys, values, rev = _table(ref_p, cr, dims)
+    qmin = torch.tensor([0, -1, -1, -1], dtype=torch.int32, device=ref_p.device)
+    out = torch.empty(query_p.shape[0], dtype=torch.int64, device=ref_p.device)
+    op.correspondence(keys, values, rev, dims, cq, query_p, qmin, -qmin, out)
     return out
+
+
+def points_in_radius(ref, query, radius):
+    """bool[N_ref]: reference points with a query strictly closer than `radius` (torch_hash_kernel.cu:160-222)."""
+    from . import torch_hash_cuda as op
+    ref_p, query_p = ops._as_points(ref), ops._as_points(query)
+    cr, cq, dims = _voxelization(ref_p, query_p, radius)
+    keys, values, rev = _table(ref_p, cr, dims)
+    qmin = torch.tensor([0, -1, -1, -1], dtype=torch.int32, device=ref_p.device)
+    visited = torch.zeros(ref_p.shape[0], dtype=torch.int64, device=ref_p.device)
+    op.points_in_radius_gpu(keys, values, rev, dims, cq, query_p, qmin, -qmin, float(radius), visited)
+    return visited.bool()
