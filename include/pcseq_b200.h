@@ -279,6 +279,9 @@ typedef struct {
   int64_t want_l1, want_ratio;
   void *nn_fwd, *nn_bwd, *boff;           /* int32[cap mv], int32[cap backward items], int32[J + 1] */
   void *mvbeg, *mvend;                    /* int32[J] scratch */
+  void *sec_fwd, *sec_bwd, *disp, *dmax;  /* optional (all or none) neighbour caching: float[cap mv], float[cap backward
+                                             items], float[cap mv], int32[J].  A query skips its search while its cached
+                                             neighbour is provably still the nearest (distance bounds, exact) */
   void *mom, *Ti, *T, *mu, *l1_sum, *l1_n; /* double [G][17], [G][12], [G][12] (out), [G][6], [G][2], [G] */
   void *phase, *cd, *iters, *itcnt;       /* int32[J] x3 (iters = iterations run, out), int32[(max_iter + 2) * 2] */
   void *last, *loss;                      /* double[J] */
@@ -286,7 +289,7 @@ typedef struct {
   void *l1_err, *ratio;                   /* double[G], float[G] outputs (want_l1 / want_ratio) */
   void *prof;                             /* optional int64[256] += ns per phase (B C D E F G H tail), [8] iterations,
                                              [9] launches, [13] / [14] moving / reference voxels searched (summed over
-                                             iterations), [16..] per-iteration search ns, [112..] active queries */
+                                             iterations), [15] searches answered from the neighbour cache, [16..] per-iteration search ns, [112..] active queries */
 } pcs_trk_icp_t;
 
 typedef struct {

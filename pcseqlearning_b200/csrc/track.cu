@@ -155,15 +155,31 @@ __device__ __forceinline__ float dist2_acc(float acc, float rx, float ry, float 
 // payload has a bit of `skipmask` set are ignored.  Returns the row's original index (warp-uniform) or -1; ties by
 // ascending index.
 // one cell swept by the warp, 32 rows per step; (best, bidx, bound) are warp-uniform on entry and on return
+// per-lane record of the two nearest rows a search has scanned (any distance): gives, after the search, a lower bound
+// of the distance to every row OTHER than the winner
+struct Near2 {
+  float d1, d2;      // smallest and second smallest squared distance seen by this lane
+  unsigned int i1;   // row of d1
+};
+
 __device__ __forceinline__ void nn_sweep(const PGrid &g, int cs, int cc, float qx, float qy, float qz, float acc0,
                                          unsigned int skipmask, int lane, unsigned long long &best, unsigned int &bidx,
-                                         float &bound) {
+                                         float &bound, Near2 *near = nullptr) {
   for (int j = lane; j < cc; j += 32) {
     const float4 p = g.sorted[cs + j];
     if (__float_as_uint(p.x) & skipmask) continue;
     const float d2 = dist2_acc(acc0, p.y, p.z, p.w, qx, qy, qz);
+    const unsigned int idx = g.sidx ? (unsigned int)g.sidx[cs + j] : (unsigned int)(cs + j);
+    if (near) {
+      if (d2 < near->d1) {
+        near->d2 = near->d1;
+        near->d1 = d2;
+        near->i1 = idx;
+      } else if (d2 < near->d2) {
+        near->d2 = d2;
+      }
+    }
     if (d2 <= bound) {
-      const unsigned int idx = g.sidx ? (unsigned int)g.sidx[cs + j] : (unsigned int)(cs + j);
       const unsigned long long k =
           ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned int)(g.tie ? g.tie[idx] : (int)idx);
       if (k < best || (k == best && idx < bidx)) {
@@ -186,12 +202,16 @@ __device__ __forceinline__ void nn_sweep(const PGrid &g, int cs, int cc, float q
 
 __device__ int nn_search(const PGrid &g, bool cursor_mode, int group, float qx, float qy, float qz, float acc0,
                          float r2, unsigned int skipmask, int lane, float *d2_out = nullptr,
-                         unsigned long long best0 = ~0ull, unsigned long long *key_out = nullptr) {
+                         unsigned long long best0 = ~0ull, unsigned long long *key_out = nullptr,
+                         float *others_lb2 = nullptr) {
   const float ux = cell_u(qx, g.lo0, g.inv_cs), uy = cell_u(qy, g.lo1, g.inv_cs), uz = cell_u(qz, g.lo2, g.inv_cs);
   const float fx = floorf(ux), fy = floorf(uy), fz = floorf(uz);
   const int cx = clamp_cell((int)fx), cy = clamp_cell((int)fy), cz = clamp_cell((int)fz);
   int start = 0, count = 0;
   unsigned int sel = 0xffffffffu;
+  const float kInf = __int_as_float(0x7f800000);
+  float lbcell = kInf;  // lower bound of the rows in this lane's cell if the cell is never swept
+  Near2 near = {kInf, kInf, 0xffffffffu};
   // best0: a known candidate (d2 bits << 32 | index) -- its distance prunes the cell lookups from the start
   if (best0 != ~0ull) r2 = fminf(r2, __uint_as_float((unsigned int)(best0 >> 32)));
   if (lane < 27) {
@@ -215,6 +235,8 @@ __device__ int nn_search(const PGrid &g, bool cursor_mode, int group, float qx, 
           count = c;
           sel = (__float_as_uint(dmin2) & ~31u) | (unsigned int)lane;
         }
+      } else {
+        lbcell = dmin2;  // pruned unseen: whatever it holds is at least this far
       }
     }
   }
@@ -233,7 +255,18 @@ __device__ int nn_search(const PGrid &g, bool cursor_mode, int group, float qx, 
     const int src = pick & 31;
     if (lane == src) sel = 0xffffffffu;
     const int cs = __shfl_sync(kAll, start, src), cc = __shfl_sync(kAll, count, src);
-    nn_sweep(g, cs, cc, qx, qy, qz, acc0, skipmask, lane, best, bidx, bound);
+    nn_sweep(g, cs, cc, qx, qy, qz, acc0, skipmask, lane, best, bidx, bound, others_lb2 ? &near : nullptr);
+  }
+  if (others_lb2) {
+    // lower bound of the squared distance to every stored row except the winner: the nearest other scanned row, the
+    // cells pruned or left unvisited, and the border of the 3x3x3 block (everything outside is a full cell away)
+    const float border = 0.98f * g.cs;
+    float lb = (best != ~0ull && near.i1 == bidx) ? near.d2 : near.d1;
+    lb = fminf(fminf(lb, lbcell), border * border + acc0);
+    if (sel != 0xffffffffu) lb = fminf(lb, __uint_as_float(sel & ~31u));  // found, but the sweep stopped before it
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lb = fminf(lb, __shfl_xor_sync(kAll, lb, o));
+    *others_lb2 = lb;
   }
   if (best == ~0ull) return -1;
   if (d2_out) *d2_out = __uint_as_float((unsigned int)(best >> 32));
@@ -289,11 +322,13 @@ __device__ void nn_search_shell(const PGrid &g, bool cursor_mode, int group, flo
 // nearest row within the radius over (2 * rings + 1)^3 cells (rings = 1 or 2: cell size >= radius / rings)
 __device__ __forceinline__ int nn_search_rings(const PGrid &g, bool cursor_mode, int group, float qx, float qy, float qz,
                                                float acc0, float r2, unsigned int skipmask, int lane, int rings,
-                                               unsigned long long best0 = ~0ull) {
+                                               unsigned long long best0 = ~0ull, float *others_lb2 = nullptr) {
   float d2 = 0.f;
   unsigned long long best = ~0ull;
-  int r = nn_search(g, cursor_mode, group, qx, qy, qz, acc0, r2, skipmask, lane, &d2, best0, &best);
+  int r = nn_search(g, cursor_mode, group, qx, qy, qz, acc0, r2, skipmask, lane, &d2, best0, &best,
+                    rings < 2 ? others_lb2 : nullptr);
   if (rings < 2) return r;
+  if (others_lb2) *others_lb2 = 0.f;  // the two-ring search keeps no bound
   float bound = r >= 0 ? d2 : r2;
   // everything outside the inner block is farther than one cell (minus the fp32 slack of the cell coordinates)
   const float cover = 0.98f * g.cs;
@@ -712,6 +747,11 @@ struct IcpB {
   int max_iter, want_l1, want_ratio;
   int *nn_fwd, *nn_bwd, *boff;
   int *mvbeg, *mvend;  // [J] rows of every instance in the moving voxel array (voxels are grouped by instance)
+  // neighbour caching: per query a lower bound (3-D metres) of the distance to every target other than its cached
+  // neighbour; per moving voxel its displacement in this iteration, per instance the largest of them (float bits)
+  float *sec_fwd, *sec_bwd, *disp;
+  int *dmax;
+  float r3skip;
   double *mom, *Ti, *T, *mu, *l1_sum, *l1_n;
   int *phase, *cd, *iters, *itcnt;
   double *last, *loss;
@@ -793,6 +833,7 @@ __global__ void __launch_bounds__(256) trk_icp_setup_kernel(IcpB A) {
   }
   if (i < A.J) {
     A.mvbeg[i] = A.mvend[i] = 0;
+    if (A.sec_fwd) A.dmax[i] = 0;
     A.phase[i] = A.act[i] ? PH_RUN : PH_FROZEN;
     A.cd[i] = 3;
     A.iters[i] = 0;
@@ -867,15 +908,37 @@ __global__ void __launch_bounds__(kTrkThreads, kMinBlocks) trk_icp_kernel(IcpB A
 
   for (int it = 0; it < A.max_iter; it++) {
     // ---- B: apply the previous transform (fp64 product stored back to fp32, :179) and count into cells --------
-    for (long long v = tid; v < nmv; v += nth) {
-      const int j = A.mv_inst[v];
-      if (A.phase[j] != PH_RUN) continue;
-      float4 p = A.mv[v];
-      if (A.iters[j] > 0) {
-        apply_T(p, A.Ti + (long long)A.mv_gid[v] * 12);
-        A.mv[v] = p;
+    for (long long v0 = tid - lane; v0 < nmv; v0 += nth) {  // warp-uniform trip count (warp collectives below)
+      const long long v = v0 + lane;
+      int j = -1;
+      float d = 0.f;
+      if (v < nmv) {
+        j = A.mv_inst[v];
+        if (A.phase[j] != PH_RUN) j = -1;
       }
-      pg_count(A.mov, j, p.y, p.z, p.w);
+      if (j >= 0) {
+        float4 p = A.mv[v];
+        if (A.iters[j] > 0) {
+          const float ox = p.y, oy = p.z, oz = p.w;
+          apply_T(p, A.Ti + (long long)A.mv_gid[v] * 12);
+          A.mv[v] = p;
+          const float dx = p.y - ox, dy = p.z - oy, dz = p.w - oz;
+          d = sqrtf(dx * dx + dy * dy + dz * dz) * 1.00001f + 1e-7f;  // never below the true displacement
+        }
+        if (A.sec_fwd) A.disp[v] = d;
+        pg_count(A.mov, j, p.y, p.z, p.w);
+      }
+      if (A.sec_fwd) {
+        // largest displacement per instance: one atomic per warp when its voxels belong to one instance
+        const int jlo = __reduce_min_sync(kAll, j < 0 ? 0x7fffffff : j), jhi = __reduce_max_sync(kAll, j);
+        const int dbits = __float_as_int(d);
+        if (jhi >= 0 && jlo == jhi) {
+          const int m = __reduce_max_sync(kAll, dbits);
+          if (lane == 0 && m > 0) atomicMax(&A.dmax[jhi], m);
+        } else if (j >= 0 && dbits > 0) {
+          atomicMax(&A.dmax[j], dbits);
+        }
+      }
     }
     grid.sync();
     ICP_PROF(0)
@@ -954,10 +1017,26 @@ __global__ void __launch_bounds__(kTrkThreads, kMinBlocks) trk_icp_kernel(IcpB A
       int res = -1;
       bool need_warp = active;
       unsigned long long pkey0 = ~0ull;  // the previous neighbour as a first candidate
+      // Neighbour caching (exact, triangle inequality): `sec` bounds the distance of every target other than the
+      // cached neighbour from below; it shrinks by whatever moved since (the query itself in the forward direction, at
+      // most dmax[instance] for the moving targets of the backward direction).  While the cached neighbour is still
+      // within the radius and strictly nearer than that bound it IS the nearest neighbour: no search.  An unmatched
+      // query (no cached neighbour) stays unmatched while the bound stays above the radius.
+      float sec = 0.f;
+      bool cached = false;
+      if (A.sec_fwd && active && it > 0) {
+        sec = (fwd ? A.sec_fwd[mi] : A.sec_bwd[b]) - (fwd ? A.disp[mi] : __int_as_float(A.dmax[j]));
+        if (prev < 0 && sec > A.r3skip) cached = true;
+      }
       if (active && prev >= 0) {
         const float4 c = fwd ? A.ref.sorted[prev] : A.mv[prev];
         const float d2p = dist2_acc(A.acc0, c.y, c.z, c.w, qx, qy, qz);
         if (d2p <= A.r2) pkey0 = ((unsigned long long)__float_as_uint(d2p) << 32) | (unsigned int)prev;
+        if (A.sec_fwd && it > 0 && d2p <= A.r2 &&
+            sqrtf(fmaxf(d2p - A.acc0, 0.f)) * 1.00001f + 1e-6f < sec) {
+          cached = true;
+          res = prev;
+        }
         if (A.mode == 1 && d2p <= A.r2 && d2p - A.acc0 <= A.cover2) {
           const unsigned long long k = fwd ? nn_search_thread(A.ref, false, A.ref_group[j], qx, qy, qz, A.acc0, d2p, skip)
                                            : nn_search_thread(A.mov, true, j, qx, qy, qz, A.acc0, d2p, 0u);
@@ -965,8 +1044,15 @@ __global__ void __launch_bounds__(kTrkThreads, kMinBlocks) trk_icp_kernel(IcpB A
           need_warp = false;
         }
       }
+      if (cached) {
+        need_warp = false;
+        if (fwd) A.sec_fwd[mi] = sec;
+        else A.sec_bwd[b] = sec;
+      }
       unsigned int todo = __ballot_sync(kAll, need_warp);
       if (A.prof) {
+        const unsigned int nc_ = __ballot_sync(kAll, cached);
+        if (lane == 0 && nc_) atomicAdd((unsigned long long *)A.prof + 15, (unsigned long long)__popc(nc_));
         const unsigned int na = __ballot_sync(kAll, active);
         if (lane == 0 && na) {
           atomicAdd((unsigned long long *)A.prof + 10, (unsigned long long)__popc(na & ~todo));
@@ -982,9 +1068,14 @@ __global__ void __launch_bounds__(kTrkThreads, kMinBlocks) trk_icp_kernel(IcpB A
         const float sx = __shfl_sync(kAll, qx, src), sy = __shfl_sync(kAll, qy, src), sz = __shfl_sync(kAll, qz, src);
         const unsigned int ss = __shfl_sync(kAll, skip, src);
         const unsigned long long sk = A.mode == 2 ? ~0ull : __shfl_sync(kAll, pkey0, src);
-        const int r = sf ? nn_search_rings(A.ref, false, A.ref_group[sj], sx, sy, sz, A.acc0, A.r2, ss, lane, A.rings, sk)
-                         : nn_search_rings(A.mov, true, sj, sx, sy, sz, A.acc0, A.r2, 0u, lane, A.rings, sk);
-        if (lane == src) res = r;
+        float olb2 = 0.f;
+        float *olb = A.sec_fwd ? &olb2 : nullptr;
+        const int r = sf ? nn_search_rings(A.ref, false, A.ref_group[sj], sx, sy, sz, A.acc0, A.r2, ss, lane, A.rings, sk, olb)
+                         : nn_search_rings(A.mov, true, sj, sx, sy, sz, A.acc0, A.r2, 0u, lane, A.rings, sk, olb);
+        if (lane == src) {
+          res = r;
+          sec = sqrtf(fmaxf(olb2 - A.acc0, 0.f)) * 0.9999f;
+        }
       }
       int c = -1;
       float4 mp = make_float4(0.f, 0.f, 0.f, 0.f), rp = mp;
@@ -992,9 +1083,11 @@ __global__ void __launch_bounds__(kTrkThreads, kMinBlocks) trk_icp_kernel(IcpB A
         if (fwd) {
           A.nn_fwd[mi] = res;
           ri = res;
+          if (A.sec_fwd && !cached) A.sec_fwd[mi] = sec;
         } else {
           A.nn_bwd[b] = res;
           mi = res;
+          if (A.sec_fwd && !cached) A.sec_bwd[b] = sec;
         }
         if (res >= 0) {
           mp = A.mv[mi];
@@ -1111,6 +1204,7 @@ __global__ void __launch_bounds__(kTrkThreads, kMinBlocks) trk_icp_kernel(IcpB A
     if (tid < A.J) {
       const int j = (int)tid;
       if (A.phase[j] == PH_FINISHING) A.phase[j] = PH_FROZEN;
+      if (A.sec_fwd) A.dmax[j] = 0;  // consumed by phase E of this iteration
       if (A.phase[j] == PH_RUN) {
         const double loss = A.loss[j], last = A.last[j];
         int cd = A.cd[j];
@@ -1788,11 +1882,12 @@ IcpB make_icp(const pcs_trk_icp_t *P) {
   A.r2 = r * r;
   A.acc0 = (float)((double)P->df * (double)P->df);
   A.rings = (int)P->rings < 2 ? 1 : 2;
+  A.r3skip = sqrtf(fmaxf(A.r2 - A.acc0, 0.f)) * 1.0005f + 1e-5f;
   {
     const char *m = getenv("PCS_ICP_MODE");
     A.mode = m ? atoi(m) : 0;
     const char *bq = getenv("PCS_ICP_BATCH");
-    A.batch = bq ? atoi(bq) : 8;
+    A.batch = bq ? atoi(bq) : 16;
     if (A.batch < 1 || A.batch > 32) A.batch = 32;
   }
   {
@@ -1809,6 +1904,11 @@ IcpB make_icp(const pcs_trk_icp_t *P) {
   A.boff = (int *)P->boff;
   A.mvbeg = (int *)P->mvbeg;
   A.mvend = (int *)P->mvend;
+  A.sec_fwd = (float *)P->sec_fwd;
+  A.sec_bwd = (float *)P->sec_bwd;
+  A.disp = (float *)P->disp;
+  A.dmax = (int *)P->dmax;
+  if (!A.sec_fwd || !A.sec_bwd || !A.disp || !A.dmax) A.sec_fwd = nullptr;  // all or none
   A.mom = (double *)P->mom;
   A.Ti = (double *)P->Ti;
   A.T = (double *)P->T;

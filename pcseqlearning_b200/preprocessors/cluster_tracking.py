@@ -616,7 +616,7 @@ class ClusterTracking(nn.Module):
                 for lv, pr in enumerate(tb.prof):
                     pr = pr.tolist()
                     print(f"[icp level {lv}] launches {pr[9]} iterations {pr[8]} thread-path {pr[10]} warp-path {pr[11]} "
-                          f"unmatched {pr[12]} " +
+                          f"unmatched {pr[12]} cached {pr[15]} " +
                           ", ".join(f"{n} {pr[i] / 1e6:.1f} ms" for i, n in enumerate(names)), flush=True)
                     if os.environ.get("PCS_TRACK_TIMING") == "2":
                         print("   per-iteration search ms (summed over launches): " +

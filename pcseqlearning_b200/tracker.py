@@ -47,6 +47,7 @@ IcpStruct = _mk_struct("pcs_trk_icp_t", [
     ("lo", _D * 3), ("cs", _D), ("rings", _I), ("radius", _D), ("df", _I), ("angle_reg", _D), ("max_iter", _I),
     ("stopping_delta", _D), ("want_l1", _I), ("want_ratio", _I),
     ("nn_fwd", _P), ("nn_bwd", _P), ("boff", _P), ("mvbeg", _P), ("mvend", _P),
+    ("sec_fwd", _P), ("sec_bwd", _P), ("disp", _P), ("dmax", _P),
     ("mom", _P), ("Ti", _P), ("T", _P), ("mu", _P), ("l1_sum", _P), ("l1_n", _P),
     ("phase", _P), ("cd", _P), ("iters", _P), ("itcnt", _P), ("last", _P), ("loss", _P), ("match_cnt", _P),
     ("l1_err", _P), ("ratio", _P), ("prof", _P)])
@@ -309,9 +310,9 @@ class TrackBatch:
                                                _ptr(keys)), "pcs_trk_cell_keys")
                 # canonical row order (cell key, then x, y, z): equal-distance ties of the searches are resolved by row,
                 # and the sampler emits voxels in a run-dependent order
-                perm = torch.arange(Vc, device=dev)
-                for col in (3, 2, 1):
-                    perm = perm[torch.sort(cat_pts[perm, col], stable=True)[1]]
+                bits = cat_pts[:, 1:].contiguous().view(torch.int32).long() & 0xffffffff
+                pos_key = ((bits[:, 0] << 32) | bits[:, 1]) ^ (bits[:, 2] << 13)  # any deterministic function of xyz
+                perm = torch.sort(pos_key)[1]
                 ks, o2 = torch.sort(keys[perm], stable=True)
                 perm = perm[o2]
                 rv = cat_pts[perm].contiguous()
@@ -409,6 +410,7 @@ class TrackBatch:
                       mov_sidx=_e(M, torch.int32, dev), mov_cells=_e(M, torch.int32, dev), mov_ctr=_z(4, torch.int32, dev),
                       nn_fwd=_e(M, torch.int32, dev), boff=_z(J + 1, torch.int32, dev),
                       mvbeg=_z(J, torch.int32, dev), mvend=_z(J, torch.int32, dev),
+                      sec_fwd=_z(M, torch.float32, dev), disp=_z(M, torch.float32, dev), dmax=_z(J, torch.int32, dev),
                       mom=_z((G, 17), torch.float64, dev), Ti=_z((G, 12), torch.float64, dev), mu=_z((G, 6), torch.float64, dev),
                       l1_sum=_z((G, 2), torch.float64, dev), l1_n=_z(G, torch.float64, dev),
                       phase=_z(J, torch.int32, dev), cd=_z(J, torch.int32, dev), iters=_z(J, torch.int32, dev),
@@ -417,6 +419,9 @@ class TrackBatch:
             _lib.check(L.pcs_trk_table_clear(s, _ptr(sc["mov_table"]), Hm, _ptr(sc["mov_ctr"])), "pcs_trk_table_clear")
             self.sc = sc
             nn_bwd = _e(max(lv["bwd_cap"] for lv in self.levels), torch.int32, dev)
+            sec_bwd = _z(max(lv["bwd_cap"] for lv in self.levels), torch.float32, dev)
+            if __import__('os').environ.get('PCS_ICP_NOCACHE'):
+                sc['sec_fwd'] = None
             self.skipmask = torch.zeros(J, dtype=torch.int32, device=dev)  # the grids hold non-stationary voxels only
             self.prof = [_z(256, torch.int64, dev) for _ in range(self.n_levels)]
             icp_arr = (IcpStruct * self.n_levels)()
@@ -429,7 +434,7 @@ class TrackBatch:
                       n_mv=self.sampler.t["ctr"][1:], vdeg=t["vdeg"], lo=lo, cs=d["cs"], rings=ICP_RINGS,
                       radius=self.radius[lv], df=0,
                       angle_reg=self.angle_reg, max_iter=80, stopping_delta=self.stopping_delta[lv], want_l1=0,
-                      want_ratio=0, nn_bwd=nn_bwd, T=t["T"], l1_err=t["l1_err"], ratio=t["ratio"], prof=self.prof[lv], **sc)
+                      want_ratio=0, nn_bwd=nn_bwd, sec_bwd=sec_bwd, T=t["T"], l1_err=t["l1_err"], ratio=t["ratio"], prof=self.prof[lv], **sc)
             self.icp_arr = icp_arr
 
     # ----------------------------------------------------------------------------------------------------------
@@ -594,6 +599,8 @@ def register_pair(mov_fxyz, mov_comp, mov_stationary, ref_fxyz, ref_stationary, 
                       mov_sidx=_e(nm, torch.int32, dev), mov_cells=_e(nm, torch.int32, dev), mov_ctr=_z(4, torch.int32, dev),
                       nn_fwd=_e(nm, torch.int32, dev), nn_bwd=_e(max(n_ns, 1), torch.int32, dev),
                       boff=_z(2, torch.int32, dev), mvbeg=_z(1, torch.int32, dev), mvend=_z(1, torch.int32, dev),
+                      sec_fwd=_z(nm, torch.float32, dev), sec_bwd=_z(max(n_ns, 1), torch.float32, dev),
+                      disp=_z(nm, torch.float32, dev), dmax=_z(1, torch.int32, dev),
                       mom=_z((C, 17), torch.float64, dev), Ti=_z((C, 12), torch.float64, dev),
                       mu=_z((C, 6), torch.float64, dev), l1_sum=_z((C, 2), torch.float64, dev), l1_n=_z(C, torch.float64, dev),
                       phase=_z(1, torch.int32, dev), cd=_z(1, torch.int32, dev), iters=iters,
