@@ -16,9 +16,10 @@ preprocessors).
          the timed region
   roofline / cpu_baseline / clocks / gpu_launches: see DESIGN.md
 
-N > 1 (torchrun, one rank per GPU): default = every rank processes its own sequence (replicas, "weak" scaling,
-the reference's DDP-over-sequences); --shard frames = ONE sequence sharded by frame windows with NCCL halo
-exchange ("strong" scaling, BASELINE.json configs[3]).
+N > 1 (torchrun, one rank per GPU): default (--shard frames) = ONE sequence sharded by frame windows with NCCL
+halo exchange ("strong" scaling, BASELINE.json configs[3]); the replica throughput (every rank its own sequence,
+the reference's DDP-over-sequences, configs[4]) is measured in the same run and reported in config.replicas.
+--shard none makes the replicas the headline ("weak" scaling).
 """
 import argparse
 import gc
@@ -213,6 +214,7 @@ def run_ours(args, rank, world, local_rank):
         # 10-frame chunks; ground-stage voxel sums, halo frames and IoU maxima travel over NCCL inside the step
         from pcseqlearning_b200 import parallel
         shard = parallel.set_sharding(parallel.FrameSharding(args.frames))
+        full_batch = batch
         batch = window_batch(batch, *shard.window)
         torch.cuda.synchronize()
     model = build_model(dev)
@@ -370,6 +372,20 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0 and world == 1 and not args.no_ref_kernel:
         roofline["reference_kernel"] = reference_kernel_ms(seq, rs_total_ms=sum(durs) / max(args.steps, 1))
 
+    n_sub, n_g = int(seq["full_point_fxyz"].shape[0]), int(seq["point_fxyz"].shape[0])
+    replicas = None
+    if sharded:
+        # the same box as replicas (config 5 style: one whole sequence per rank, no data-path collective)
+        from pcseqlearning_b200 import parallel as _par
+        _par.set_sharding(None)
+        batch = full_batch
+        seq = seq_e = None
+        for _ in range(2):
+            step_device()
+        ms_rep, _ = timed(step_device, args.steps)
+        replicas = {"value": round(args.frames * world / (ms_rep / args.steps / 1e3), 3), "unit": UNIT,
+                    "ms_per_step": round(ms_rep / args.steps, 3), "scaling": "weak",
+                    "parallelism": "replicas (one sequence per rank, no collective)"}
     frames_total = args.frames if sharded else args.frames * world
     value = frames_total / (ms_dev / args.steps / 1e3)
     e2e = frames_total / (ms_e2e / args.steps / 1e3)
@@ -379,13 +395,13 @@ def run_ours(args, rank, world, local_rank):
         "higher_is_better": True,
         "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "frames": args.frames, "points_per_sequence": n_points,
-                   "points_after_subsample": int(seq["full_point_fxyz"].shape[0]),
-                   "points_after_ground_removal": int(seq["point_fxyz"].shape[0]),
+                   "points_after_subsample": n_sub, "points_after_ground_removal": n_g,
                    "points_per_s": round(n_points * world / (ms_dev / args.steps / 1e3)),
                    "l2": "inputs (%.0f MB per step) larger than L2" % (h2d_bytes / 1e6),
                    "parallelism": ("frame-windows (one sequence; NCCL: ground voxel sums, +-8-frame halo all-to-all, "
                                    "IoU max-merge)" if sharded else ("replicas" if world > 1 else "single")),
                    "generate_s": round(gen_s, 1)},
+        **({"replicas": replicas} if replicas is not None else {}),
         "e2e": {"value": round(e2e, 3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": int(out_e),
                 "ms_per_step": round(ms_e2e / args.steps, 3),
@@ -680,8 +696,9 @@ def main():
                     help="CPU arm: track every instance instead of cutting the tracker after %.0f s" % TRACK_BUDGET_S)
     ap.add_argument("--no-ref-kernel", action="store_true", dest="no_ref_kernel",
                     help="skip timing the reference's own CUDA op (the kernel to beat)")
-    ap.add_argument("--shard", default="none", choices=["none", "frames"],
-                    help="N > 1: 'frames' shards ONE sequence by frame windows (strong scaling)")
+    ap.add_argument("--shard", default="frames", choices=["none", "frames"],
+                    help="N > 1: 'frames' (default) shards ONE sequence by frame windows (strong scaling); 'none' runs "
+                         "one sequence per rank (replicas, weak scaling)")
     ap.add_argument("--cache", default=None, help="path prefix to cache the synthetic sequence (profiling runs)")
     ap.add_argument("--no-cpu-baseline", action="store_true", dest="no_cpu")
     args = ap.parse_args()

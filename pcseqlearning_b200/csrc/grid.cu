@@ -149,7 +149,11 @@ __device__ __forceinline__ long long find_or_insert(pcs_slot_t *table, long long
                                                     int *counters, unsigned int *occ, int occ_shift) {
   const unsigned int h = hash_key(key);
   long long slot = h & mask;
-  for (long long probes = 0; probes <= mask; ++probes) {
+  // A probe sequence this long means the table is (nearly) full: give up and flag it instead of walking the whole
+  // table for every remaining point (an under-sized table cost 600 ms that way before the caller could rebuild it).
+  const long long max_probes = mask < 8192 ? mask : 8192;
+  for (long long probes = 0; probes <= max_probes; ++probes) {
+    if ((probes & 255) == 255 && *((volatile int *)&counters[2]) != 0) return -1;  // someone already flagged it
     long long cur = *((volatile long long *)&table[slot].key);
     if (cur == key) return slot;
     if (cur == PCS_EMPTY_KEY) {

@@ -317,14 +317,19 @@ def compact_grid(points, voxel_size, **kw):
     to clear / scan and L2-resident lookups).  The build reports overflow through its error flag; in that case the
     grid is rebuilt with the always-sufficient default size.  Costs one host sync."""
     n = points.shape[0]
-    small = next_pow2(max(n // 4, 1024))
+    small = next_pow2(max(n // 2, 1024))  # cells / points is ~0.45 at r = 0.25 m, far less for the larger radii
     if GRID_SORTED:
         kw = dict(kw, sorted_cells=True)
     grid = CellGrid(points, voxel_size, table_size=small, **kw)
-    code = int(grid.counters[2].item())
+    cells, _, code, _ = grid.counters.tolist()  # host sync
     if code == _lib.PCS_ERR_TABLE_FULL:
         grid = CellGrid(points, voxel_size, **kw)
-        code = int(grid.counters[2].item())
+        cells, _, code, _ = grid.counters.tolist()
+    elif code == 0 and 2 * cells > small:
+        # more than half full: linear probing degrades quickly (0.9 load = tens of probes per lookup, measured as a
+        # 30x slower search on a frame-window shard).  Rebuild at a load factor <= 1/3.
+        grid = CellGrid(points, voxel_size, table_size=next_pow2(3 * cells), **kw)
+        cells, _, code, _ = grid.counters.tolist()
     if code != 0:  # key range overflow etc.: a rebuild cannot help
         raise _lib.PcsError(f"voxel hash build failed on device (code {code})")
     return grid
@@ -580,11 +585,23 @@ def cluster_labels_multi(fxyz, radii, max_num_neighbors=32, chunk=10, num_frames
     # forest and the next one starts from a copy of it.
     parents = []
     cnt = None
+    dbg = os.environ.get("PCS_STAGE_TIMING")
     for i, r in enumerate(r_sorted):
+        if dbg:
+            import time
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
         parent = uf_new(n, fxyz.device) if i == 0 else parents[-1].clone()
         grid = compact_grid(fxyz, radius_voxel_size(r), seg_div=chunk, n_seg=n_seg)
+        if dbg:
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
         _, cnt, _ = grid.search(None, K, r, uf_parent=parent, want_lists=False, skip_full_cnt=cnt, cnt_out=cnt)
         parents.append(parent)
+        if dbg:
+            torch.cuda.synchronize()
+            print(f"[labels_multi] r={r} grid {1e3 * (t1 - t0):.1f} ms (H={grid.H}, cells={int(grid.counters[0])}), "
+                  f"search {1e3 * (time.perf_counter() - t1):.1f} ms", flush=True)
     seg_of = point_segments(fxyz, chunk, n_seg)
     labels, n_comp = [None] * len(radii), [None] * len(radii)
     for pos, i in enumerate(order):

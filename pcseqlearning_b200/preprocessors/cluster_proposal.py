@@ -148,7 +148,16 @@ class ClusterProposal(nn.Module):
         return seq_dict
 
     def forward(self, seq_dict):
+        import os
+        import time
+        timing = os.environ.get("PCS_STAGE_TIMING")
+        if timing:
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
         seq_dict = self.propose_cluster(seq_dict)
+        if timing:
+            torch.cuda.synchronize()
+            print(f"[proposal] propose_cluster {1e3 * (time.perf_counter() - t0):.1f} ms", flush=True)
         if self.model_cfg.get("EVALUATE", True):
             with Timer("Evaluate Proposal", verbose=self.model_cfg.get("VERBOSE", True)):
                 seq_dict = self.evaluate_proposal(seq_dict)

@@ -247,13 +247,26 @@ def ground_plane_removal(point_fxyz, cfg, warmup=None, use_kernels=True):
 
     Returns (height [N], horizon [N] bool, fitting_error [N], pillar_height [X,Y], pillar_min_z [X,Y]).
     """
+    import os
+    import time
+    timing = os.environ.get("PCS_STAGE_TIMING")
+    marks = []
+
+    def mark(name):
+        if timing:
+            torch.cuda.synchronize()
+            marks.append((name, time.perf_counter()))
+
+    mark("start")
     pillar_size = torch.tensor(cfg.PILLAR_SIZE).to(point_fxyz)
     pc_range_min = point_fxyz[:, 1:3].min(0)[0] if point_fxyz.shape[0] else point_fxyz.new_full((2,), 1e30)
     if parallel.SHARD is not None:
         pc_range_min = -parallel.SHARD.all_reduce_max(-pc_range_min)
     pc_range_min = pc_range_min - 0.05
     voxels, point_voxel_index = grid_sample(point_fxyz, [0.10, 0.10, 0.03])
+    mark("grid_sample")
     pillar_dims, num_pillars, voxels, pillars = format_pillars(voxels, pillar_size, pc_range_min)
+    mark("format_pillars")
     if warmup is not None:
         pillars.height = warmup["pillar_height"]
         pillars.min_z = warmup["pillar_min_z"]
@@ -261,8 +274,10 @@ def ground_plane_removal(point_fxyz, cfg, warmup=None, use_kernels=True):
         if cfg.get("RANSAC", False):
             voxels, pillars = compute_min_height_from_ransac(pillar_dims, num_pillars, voxels, pillars, cfg,
                                                              use_kernels=use_kernels)
+        mark("ransac")
         if cfg.get("JointOpt", False):
             pillars = l1_minimization(pillars, pillar_dims, cfg, use_kernels=use_kernels)
+        mark("l1")
         if "height" not in pillars:
             pillars.height = pillars.min_z.clone()
     cx, cy = voxels.pillar_coords[:, 0], voxels.pillar_coords[:, 1]
@@ -271,5 +286,9 @@ def ground_plane_removal(point_fxyz, cfg, warmup=None, use_kernels=True):
     v_horizon = voxels.bxyz[:, -1] > v_min_z
     v_height = voxels.bxyz[:, -1] - v_height
     fitting_error = v_height - v_min_z
+    if timing:
+        mark("end")
+        print("[ground] " + ", ".join(f"{n} {1e3 * (t - marks[i][1]):.1f} ms" for i, (n, t) in enumerate(marks[1:])),
+              flush=True)
     return (ops.gather_rows(v_height, point_voxel_index), ops.gather_rows(v_horizon, point_voxel_index),
             ops.gather_rows(fitting_error, point_voxel_index), pillars.height, pillars.min_z)

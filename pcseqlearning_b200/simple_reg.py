@@ -82,9 +82,17 @@ class SimpleReg(RegistrationTemplate):
         self.subsample_grid = [0.08, 0.08, 0.08]  # simple_reg.py:24
 
     def process_sequence(self, seq_dict):
+        timing = os.environ.get("PCS_STAGE_TIMING")
         if self.preprocessors:
             for module in self.preprocessors:
+                if timing:
+                    import time
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
                 seq_dict = module(seq_dict)
+                if timing:
+                    torch.cuda.synchronize()
+                    print(f"[stage] {type(module).__name__} {1e3 * (time.perf_counter() - t0):.1f} ms", flush=True)
         return seq_dict
 
     def format_boxes(self, seq_dict):
