@@ -371,13 +371,68 @@ def gen_eval_tracking():
           "boxes", seq_boxes.attr.shape, "best_iou max", float(seq_boxes.best_iou.max()), "calls", len(calls), "picked", len(pick))
 
 
+
+def gen_fullscale():
+    """Config-scale fixtures (BASELINE.json configs: 64 beams x 2650 azimuth steps): two frames at full density through
+    the reference's ClusterProposal.propose_cluster (3 radii: 1.25 m cells hold thousands of points there and the
+    K = 32 truncation is active) and one full-density frame pair through sample_frame + register_to_next_frame."""
+    import time
+    cp = R.load("pcdet.models.registration.preprocessors.cluster_proposal")
+    ct = R.load("pcdet.models.registration.preprocessors.cluster_tracking")
+    ru = R.load("pcdet.models.registration.preprocessors.registration_utils")
+    gs = R.load("pcdet.models.model_utils.grid_sampling")
+    gu = R.load("pcdet.models.model_utils.graph_utils")
+    from . import cpu_ops as ops
+    b, f, seg = _scene(0, 2, 64, 2650)
+    pick = ops.subsample_pick(f.numpy())
+    f, seg = f[torch.from_numpy(pick)], seg[torch.from_numpy(pick)]
+    keep = seg < 17
+    f = f[keep].contiguous()
+    sweep = f[:, 0].round().int().reshape(-1, 1)
+    cfg = R.edict(GRAPH=dict(TYPE="RadiusGraph", RADIUS=[1.25, 0.75, 0.25], MAX_NUM_NEIGHBORS=32, SORT_BY_DIST=True,
+                             RELATIVE_KEY="fxyz"),
+                  COMPONENT_KEYS=["component_rad1x25", "component_rad0x75", "component_rad0x25"], DIR=tempfile.mkdtemp())
+    mod = cp.ClusterProposal(runtime_cfg={}, model_cfg=cfg)
+    t0 = time.time()
+    seq = mod.propose_cluster(R.edict(point_fxyz=f.clone(), point_sweep=sweep.clone(), frame_id=np.array(["full_000"])))
+    print(f"reference propose_cluster on {f.shape[0]} points took {time.time() - t0:.1f}s")
+    out = dict(points=f.numpy())
+    for k in cfg.COMPONENT_KEYS:
+        out[k] = seq[f"point_{k}"].numpy()
+    # one ICP pair at full density, levels 0 and 2
+    comp = seq["point_component_rad0x75"]
+    fr = f[:, 0].round().long()
+    diam = ct.component_diameter(R.edict(fxyz=f, component=comp))[comp]
+    stat = diam > 12.5
+    a = R.edict(fxyz=f[fr == 0].clone(), component=(comp[fr == 0] - comp[fr == 0].min()), frame=sweep[fr == 0].clone(),
+                stationary=stat[fr == 0].clone())
+    nb = R.edict(fxyz=f[fr == 1].clone(), component=comp[fr == 1].clone(), frame=sweep[fr == 1].clone(),
+                 stationary=stat[fr == 1].clone())
+    C = int(a.component.max()) + 1
+    for lvl, (radius, vs) in {0: (2.5, [0.4, 0.4, 0.6]), 2: (1.0, [0.1, 0.1, 0.15])}.items():
+        sampler = gs.GridSampling3D(vs)
+        sa, sb = ct.sample_frame(sampler, a), ct.sample_frame(sampler, nb)
+        g = gu.RadiusGraph(runtime_cfg={}, model_cfg=dict(RADIUS=radius, MAX_NUM_NEIGHBORS=1, SORT_BY_DIST=True,
+                                                          RELATIVE_KEY="fxyz"))
+        p = f"icp_l{lvl}_"
+        out.update({p + "mov": sa.fxyz.clone().numpy(), p + "mov_comp": sa.component.clone().numpy(),
+                    p + "mov_stat": sa.stationary.clone().numpy(), p + "ref": sb.fxyz.clone().numpy(),
+                    p + "ref_stat": sb.stationary.clone().numpy(), p + "C": np.array(C), p + "radius": np.array(radius)})
+        t0 = time.time()
+        mv, T, l1, ratio = ru.register_to_next_frame(g, sa, sb, C, 10, max_iter=80, stopping_delta=0.05)
+        print(f"reference register_to_next_frame level {lvl}: {sa.fxyz.shape[0]} x {sb.fxyz.shape[0]} voxels, "
+              f"{time.time() - t0:.1f}s")
+        out.update({p + "T": T.numpy(), p + "l1": l1.numpy(), p + "ratio": ratio.numpy()})
+    np.savez_compressed(os.path.join(OUT, "fullscale.npz"), **out)
+    print("fullscale.npz", f.shape, {k: int(out[k].max()) + 1 for k in cfg.COMPONENT_KEYS})
+
 def main():
     """python -m oracle.gen_golden [name ...]   (default: every fixture)"""
     import sys
     os.makedirs(OUT, exist_ok=True)
     gens = dict(radius_graph=gen_radius_graph, grid_sampling=gen_grid_sampling, proposal=gen_proposal,
                 registration=gen_registration, ground=gen_ground, tracking=gen_tracking,
-                eval_tracking=gen_eval_tracking)
+                eval_tracking=gen_eval_tracking, fullscale=gen_fullscale)
     for name in (sys.argv[1:] or list(gens)):
         torch.manual_seed(0)
         gens[name]()

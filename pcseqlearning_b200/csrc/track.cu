@@ -980,7 +980,10 @@ __global__ void __launch_bounds__(kTrkThreads, kMinBlocks) trk_icp_kernel(IcpB A
       A.prof[14] += nb;
     }
     const int n_active = s_aoff[A.J];
-    const int BQ = A.batch;  // work items per warp batch (<= 32)
+    // work items per warp batch (<= 32): the items of a batch are searched one after the other by the warp, so in
+    // the long tail of an ICP (few instances still iterating) smaller batches spread the latency chains over all warps
+    int BQ = (int)(((long long)n_active + nwarps - 1) / nwarps);
+    BQ = BQ < 1 ? 1 : (BQ > A.batch ? A.batch : BQ);
     const long long nbatch = ((long long)n_active + BQ - 1) / BQ;
     // consecutive batches go to different CTAs (SMs): the costly regions of the item axis are spread over the chip
     for (long long batch = (long long)(threadIdx.x >> 5) * gridDim.x + blockIdx.x; batch < nbatch; batch += nwarps) {
