@@ -142,3 +142,70 @@ def test_synthetic_dataset_plugin_contract():
     n0 = ds[0]["point_wise"]["point_xyz"].shape[0]
     assert two["batch_size"] == 2 and (two["point_bxyz"][:n0, 0] == 0).all() and (two["point_bxyz"][n0:, 0] == 1).all()
     assert two["gt_box_attr"].shape[0] == 2
+
+
+def test_chunk_windows_and_anchor_blocks():
+    for num_frames in (16, 198, 40, 7, 400):
+        for world in (1, 2, 4, 8):
+            w = parallel.chunk_windows(num_frames, world)
+            assert sum((list(range(s, e)) for s, e in w), []) == list(range(num_frames))
+            assert all(s % 10 == 0 or s == num_frames for s, _ in w)
+            blocks = parallel.anchor_blocks(num_frames, world)
+            assert sum(blocks, []) == list(range(0, num_frames, 8))
+            sizes = [len(b) for b in blocks]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _shard_worker(rank, world, port, num_frames, workdir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sh = parallel.FrameSharding(num_frames)
+    data = np.load(os.path.join(workdir, "in.npz"))
+    frame_all, val_all, flag_all = data["frame"], data["val"], data["flag"]
+    own = (frame_all >= sh.window[0]) & (frame_all < sh.window[1])
+    frame = torch.from_numpy(frame_all[own])
+    out, fr = sh.exchange_frames(dict(val=torch.from_numpy(val_all[own]), flag=torch.from_numpy(flag_all[own])), frame)
+    lo, hi = sh.need[rank]
+    want = (frame_all >= lo) & (frame_all < hi)
+    # a single process selects the needed frames in ascending frame order keeping the row order inside a frame
+    order = np.argsort(frame_all[want], kind="stable")
+    ok_halo = (np.array_equal(fr.numpy(), frame_all[want][order]) and np.array_equal(out["val"].numpy(), val_all[want][order])
+               and np.array_equal(out["flag"].numpy(), flag_all[want][order]) and out["flag"].dtype == torch.bool)
+    # bounds: order-preserving uint32 encodings carried in an int32 tensor, min over the first 4 / max over the last 4
+    enc = np.array([[5 + rank, 2 ** 31 + 7 - rank, 1, 9, 100 + rank, 2 ** 32 - 1 - rank, 3, 2 ** 31 + rank]], np.uint32)
+    b = torch.from_numpy(enc.view(np.int32).copy())
+    sh.reduce_bounds(b)
+    got = b.numpy().view(np.uint32)[0].tolist()
+    ok_bounds = got == [5, 2 ** 31 + 7 - (world - 1), 1, 9, 100 + world - 1, 2 ** 32 - 1, 3, 2 ** 31 + world - 1]
+    cat, sizes = sh.all_gather_v(torch.full((rank + 2, 3), float(rank)))
+    ok_gather = sizes == [r + 2 for r in range(world)] and cat.shape[0] == sum(sizes) and \
+        all(bool((cat[sum(sizes[:r]):sum(sizes[:r + 1])] == r).all()) for r in range(world))
+    mx = sh.all_reduce_max(torch.tensor([float(rank), 3.0 - rank]))
+    sm = sh.all_reduce_sum(torch.tensor([1, rank]))
+    ok_red = mx.tolist() == [world - 1.0, 3.0] and sm.tolist() == [world, world * (world - 1) // 2]
+    res = torch.tensor([int(ok_halo), int(ok_bounds), int(ok_gather), int(ok_red)])
+    dist.all_reduce(res, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        np.save(os.path.join(workdir, "shard_result.npy"), res.numpy())
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("num_frames", [48, 23])
+def test_frame_sharding_collectives_two_ranks(tmp_path, num_frames):
+    """FrameSharding on gloo: the halo exchange hands every rank exactly the rows a single process would select for
+    [first anchor - 8, last anchor + 8]; bounds / max / sum reductions and the variable-length gather."""
+    rng = np.random.default_rng(3)
+    n = 4000
+    frame = np.sort(rng.integers(0, num_frames, n)).astype(np.int64)
+    frame = frame[rng.permutation(n)] if num_frames == 23 else frame  # unsorted rows inside a window too
+    np.savez(os.path.join(tmp_path, "in.npz"), frame=frame, val=rng.normal(size=(n, 4)).astype(np.float32),
+             flag=rng.random(n) < 0.3)
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    procs = [ctx.Process(target=_shard_worker, args=(r, 2, port, num_frames, str(tmp_path))) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert np.load(os.path.join(tmp_path, "shard_result.npy")).tolist() == [1, 1, 1, 1]
