@@ -283,7 +283,7 @@ typedef struct {
                                              items], float[cap mv], int32[J].  A query skips its search while its cached
                                              neighbour is provably still the nearest (distance bounds, exact) */
   void *mom, *Ti, *T, *mu, *l1_sum, *l1_n; /* double [G][17], [G][12], [G][12] (out), [G][6], [G][2], [G] */
-  void *phase, *cd, *iters, *itcnt;       /* int32[J] x3 (iters = iterations run, out), int32[(max_iter + 2) * 2] */
+  void *phase, *cd, *iters, *itcnt;       /* int32[J] x3 (iters = iterations run, out), int32[(max_iter + 2) * 3] */
   void *last, *loss;                      /* double[J] */
   void *match_cnt;                        /* int32[G] */
   void *l1_err, *ratio;                   /* double[G], float[G] outputs (want_l1 / want_ratio) */

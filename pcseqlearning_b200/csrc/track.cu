@@ -162,9 +162,22 @@ struct Near2 {
   unsigned int i1;   // row of d1
 };
 
+// warp-wide minimum of (best, bidx) in the order (d2, tie key, row)
+__device__ __forceinline__ void nn_reduce_best(unsigned long long &best, unsigned int &bidx) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long t = __shfl_xor_sync(kAll, best, o);
+    const unsigned int ti = __shfl_xor_sync(kAll, bidx, o);
+    if (t < best || (t == best && ti < bidx)) {
+      best = t;
+      bidx = ti;
+    }
+  }
+}
+
 __device__ __forceinline__ void nn_sweep(const PGrid &g, int cs, int cc, float qx, float qy, float qz, float acc0,
                                          unsigned int skipmask, int lane, unsigned long long &best, unsigned int &bidx,
-                                         float &bound, Near2 *near = nullptr) {
+                                         float &bound, Near2 *near = nullptr, bool lazy = false) {
   for (int j = lane; j < cc; j += 32) {
     const float4 p = g.sorted[cs + j];
     if (__float_as_uint(p.x) & skipmask) continue;
@@ -188,22 +201,21 @@ __device__ __forceinline__ void nn_sweep(const PGrid &g, int cs, int cc, float q
       }
     }
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const unsigned long long t = __shfl_xor_sync(kAll, best, o);
-    const unsigned int ti = __shfl_xor_sync(kAll, bidx, o);
-    if (t < best || (t == best && ti < bidx)) {
-      best = t;
-      bidx = ti;
-    }
+  if (lazy) {
+    // (best, bidx) stay per lane (nn_reduce_best merges them once, after the last cell); only the pruning bound is
+    // shared: the smallest distance any lane holds (non-negative floats order like their bit patterns)
+    const unsigned int m = __reduce_min_sync(kAll, (unsigned int)(best >> 32));
+    if (m != 0xffffffffu) bound = fminf(bound, __uint_as_float(m));
+    return;
   }
+  nn_reduce_best(best, bidx);
   if (best != ~0ull) bound = fminf(bound, __uint_as_float((unsigned int)(best >> 32)));
 }
 
 __device__ int nn_search(const PGrid &g, bool cursor_mode, int group, float qx, float qy, float qz, float acc0,
                          float r2, unsigned int skipmask, int lane, float *d2_out = nullptr,
                          unsigned long long best0 = ~0ull, unsigned long long *key_out = nullptr,
-                         float *others_lb2 = nullptr) {
+                         float *others_lb2 = nullptr, float margin = 0.f) {
   const float ux = cell_u(qx, g.lo0, g.inv_cs), uy = cell_u(qy, g.lo1, g.inv_cs), uz = cell_u(qz, g.lo2, g.inv_cs);
   const float fx = floorf(ux), fy = floorf(uy), fz = floorf(uz);
   const int cx = clamp_cell((int)fx), cy = clamp_cell((int)fy), cz = clamp_cell((int)fz);
@@ -213,7 +225,16 @@ __device__ int nn_search(const PGrid &g, bool cursor_mode, int group, float qx, 
   float lbcell = kInf;  // lower bound of the rows in this lane's cell if the cell is never swept
   Near2 near = {kInf, kInf, 0xffffffffu};
   // best0: a known candidate (d2 bits << 32 | index) -- its distance prunes the cell lookups from the start
+  const float r2_full = r2;
   if (best0 != ~0ull) r2 = fminf(r2, __uint_as_float((unsigned int)(best0 >> 32)));
+  // margin > 0 (neighbour caching): cells up to `margin` metres beyond the current best distance are swept as well.
+  // They cannot hold a better row, but their rows then enter the lower bound of "every other row" exactly instead of
+  // through the distance to the cell wall, which for a query next to a wall is no bound at all.
+  float r2_look = r2;
+  if (margin > 0.f) {
+    const float e = sqrtf(fmaxf(r2 - acc0, 0.f)) + margin;
+    r2_look = fminf(r2_full, e * e + acc0);
+  }
   if (lane < 27) {
     const int ox = lane % 3 - 1, oy = (lane / 3) % 3 - 1, oz = lane / 9 - 1;
     const int nx = cx + ox, ny = cy + oy, nz = cz + oz;
@@ -228,7 +249,7 @@ __device__ int nn_search(const PGrid &g, bool cursor_mode, int group, float qx, 
       gy = (oy != 0 && gy > 0.f) ? gy * g.cs : 0.f;
       gz = (oz != 0 && gz > 0.f) ? gz * g.cs : 0.f;
       const float dmin2 = (gx * gx + gy * gy + gz * gz + acc0) * 0.99999f;
-      if (dmin2 <= r2) {
+      if (dmin2 <= r2_look) {
         int s = 0, c = 0;
         if (pg_lookup(g, pkey(group, nx, ny, nz), s, c) && c > 0) {
           start = cursor_mode ? s - c : s;
@@ -251,12 +272,18 @@ __device__ int nn_search(const PGrid &g, bool cursor_mode, int group, float qx, 
   while (true) {
     const unsigned int pick = __reduce_min_sync(kAll, sel);
     if (pick == 0xffffffffu) break;
-    if (__uint_as_float(pick & ~31u) > bound) break;
+    float reach = bound;
+    if (margin > 0.f) {
+      const float e = sqrtf(fmaxf(bound - acc0, 0.f)) + margin;
+      reach = fminf(r2_full, e * e + acc0);
+    }
+    if (__uint_as_float(pick & ~31u) > reach) break;
     const int src = pick & 31;
     if (lane == src) sel = 0xffffffffu;
     const int cs = __shfl_sync(kAll, start, src), cc = __shfl_sync(kAll, count, src);
-    nn_sweep(g, cs, cc, qx, qy, qz, acc0, skipmask, lane, best, bidx, bound, others_lb2 ? &near : nullptr);
+    nn_sweep(g, cs, cc, qx, qy, qz, acc0, skipmask, lane, best, bidx, bound, others_lb2 ? &near : nullptr, true);
   }
+  nn_reduce_best(best, bidx);
   if (others_lb2) {
     // lower bound of the squared distance to every stored row except the winner: the nearest other scanned row, the
     // cells pruned or left unvisited, and the border of the 3x3x3 block (everything outside is a full cell away)
@@ -264,9 +291,7 @@ __device__ int nn_search(const PGrid &g, bool cursor_mode, int group, float qx, 
     float lb = (best != ~0ull && near.i1 == bidx) ? near.d2 : near.d1;
     lb = fminf(fminf(lb, lbcell), border * border + acc0);
     if (sel != 0xffffffffu) lb = fminf(lb, __uint_as_float(sel & ~31u));  // found, but the sweep stopped before it
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) lb = fminf(lb, __shfl_xor_sync(kAll, lb, o));
-    *others_lb2 = lb;
+    *others_lb2 = __uint_as_float(__reduce_min_sync(kAll, __float_as_uint(lb)));  // lb >= 0: bit patterns order
   }
   if (best == ~0ull) return -1;
   if (d2_out) *d2_out = __uint_as_float((unsigned int)(best >> 32));
@@ -322,11 +347,12 @@ __device__ void nn_search_shell(const PGrid &g, bool cursor_mode, int group, flo
 // nearest row within the radius over (2 * rings + 1)^3 cells (rings = 1 or 2: cell size >= radius / rings)
 __device__ __forceinline__ int nn_search_rings(const PGrid &g, bool cursor_mode, int group, float qx, float qy, float qz,
                                                float acc0, float r2, unsigned int skipmask, int lane, int rings,
-                                               unsigned long long best0 = ~0ull, float *others_lb2 = nullptr) {
+                                               unsigned long long best0 = ~0ull, float *others_lb2 = nullptr,
+                                               float margin = 0.f) {
   float d2 = 0.f;
   unsigned long long best = ~0ull;
   int r = nn_search(g, cursor_mode, group, qx, qy, qz, acc0, r2, skipmask, lane, &d2, best0, &best,
-                    rings < 2 ? others_lb2 : nullptr);
+                    rings < 2 ? others_lb2 : nullptr, rings < 2 ? margin : 0.f);
   if (rings < 2) return r;
   if (others_lb2) *others_lb2 = 0.f;  // the two-ring search keeps no bound
   float bound = r >= 0 ? d2 : r2;
@@ -741,6 +767,7 @@ struct IcpB {
   const int *n_mv;  // device count
   const int *vdeg;  // [G] voxels per component (stationary ones included)
   float r2, acc0, cover2;
+  float margin;  // neighbour caching: extra sweep reach beyond the best distance (metres)
   int batch;
   int rings, mode;  // mode 0: warp search seeded with the previous neighbour, 1: + thread-level fast path, 2: unseeded
   double angle_reg, stopping_delta;
@@ -840,7 +867,7 @@ __global__ void __launch_bounds__(256) trk_icp_setup_kernel(IcpB A) {
     A.last[i] = 1e10;
     A.loss[i] = 0.0;
   }
-  if (i < (A.max_iter + 2) * 2) A.itcnt[i] = 0;
+  if (i < (A.max_iter + 2) * 3) A.itcnt[i] = 0;  // [..][2] finishing / running counts, then one work counter per iteration
   if (i == 0) {
     int o = 0;
     for (int j = 0; j < A.J; j++) {
@@ -985,8 +1012,26 @@ __global__ void __launch_bounds__(kTrkThreads, kMinBlocks) trk_icp_kernel(IcpB A
     int BQ = (int)(((long long)n_active + nwarps - 1) / nwarps);
     BQ = BQ < 1 ? 1 : (BQ > A.batch ? A.batch : BQ);
     const long long nbatch = ((long long)n_active + BQ - 1) / BQ;
-    // consecutive batches go to different CTAs (SMs): the costly regions of the item axis are spread over the chip
-    for (long long batch = (long long)(threadIdx.x >> 5) * gridDim.x + blockIdx.x; batch < nbatch; batch += nwarps) {
+    // Batches are handed out by a per-iteration work counter (a query costs anything between nothing -- cached -- and
+    // a multi-cell search, so static shares leave most warps waiting at the barrier for the unlucky ones); the next
+    // ticket is drawn before the current batch is processed, so its latency is hidden.  Static mode (PCS_ICP_MODE bit
+    // 2): consecutive batches go to different CTAs.
+    const bool dyn = (A.mode & 4) == 0;
+    int *wctr = A.itcnt + (A.max_iter + 2) * 2 + it;
+    long long ticket = (long long)(threadIdx.x >> 5) * gridDim.x + blockIdx.x;
+    if (dyn) {
+      int t0 = 0;
+      if (lane == 0) t0 = atomicAdd(wctr, 1);
+      ticket = __shfl_sync(kAll, t0, 0);
+    }
+    while (ticket < nbatch) {
+      const long long batch = ticket;
+      int tnext = 0;
+      if (dyn) {
+        if (lane == 0) tnext = atomicAdd(wctr, 1);
+      } else {
+        ticket += nwarps;
+      }
       const int w = (int)(batch * BQ) + lane;
       bool active = lane < BQ && w < n_active;
       bool fwd = true;
@@ -1040,7 +1085,7 @@ __global__ void __launch_bounds__(kTrkThreads, kMinBlocks) trk_icp_kernel(IcpB A
           cached = true;
           res = prev;
         }
-        if (A.mode == 1 && d2p <= A.r2 && d2p - A.acc0 <= A.cover2) {
+        if ((A.mode & 3) == 1 && d2p <= A.r2 && d2p - A.acc0 <= A.cover2) {
           const unsigned long long k = fwd ? nn_search_thread(A.ref, false, A.ref_group[j], qx, qy, qz, A.acc0, d2p, skip)
                                            : nn_search_thread(A.mov, true, j, qx, qy, qz, A.acc0, d2p, 0u);
           res = k == ~0ull ? prev : (int)(unsigned int)(k & 0xffffffffu);
@@ -1070,11 +1115,12 @@ __global__ void __launch_bounds__(kTrkThreads, kMinBlocks) trk_icp_kernel(IcpB A
         const int sj = __shfl_sync(kAll, j, src);
         const float sx = __shfl_sync(kAll, qx, src), sy = __shfl_sync(kAll, qy, src), sz = __shfl_sync(kAll, qz, src);
         const unsigned int ss = __shfl_sync(kAll, skip, src);
-        const unsigned long long sk = A.mode == 2 ? ~0ull : __shfl_sync(kAll, pkey0, src);
+        const unsigned long long sk = (A.mode & 3) == 2 ? ~0ull : __shfl_sync(kAll, pkey0, src);
         float olb2 = 0.f;
         float *olb = A.sec_fwd ? &olb2 : nullptr;
-        const int r = sf ? nn_search_rings(A.ref, false, A.ref_group[sj], sx, sy, sz, A.acc0, A.r2, ss, lane, A.rings, sk, olb)
-                         : nn_search_rings(A.mov, true, sj, sx, sy, sz, A.acc0, A.r2, 0u, lane, A.rings, sk, olb);
+        const float mg = olb ? A.margin : 0.f;
+        const int r = sf ? nn_search_rings(A.ref, false, A.ref_group[sj], sx, sy, sz, A.acc0, A.r2, ss, lane, A.rings, sk, olb, mg)
+                         : nn_search_rings(A.mov, true, sj, sx, sy, sz, A.acc0, A.r2, 0u, lane, A.rings, sk, olb, mg);
         if (lane == src) {
           res = r;
           sec = sqrtf(fmaxf(olb2 - A.acc0, 0.f)) * 0.9999f;
@@ -1132,6 +1178,7 @@ __global__ void __launch_bounds__(kTrkThreads, kMinBlocks) trk_icp_kernel(IcpB A
           }
         }
       }
+      if (dyn) ticket = __shfl_sync(kAll, tnext, 0);
     }
     grid.sync();
     if (A.prof && tid == 0 && it < 96) A.prof[16 + it] += gtime() - t_prev;
@@ -1889,6 +1936,8 @@ IcpB make_icp(const pcs_trk_icp_t *P) {
   {
     const char *m = getenv("PCS_ICP_MODE");
     A.mode = m ? atoi(m) : 0;
+    const char *mg = getenv("PCS_ICP_MARGIN");  // fraction of the cell size
+    A.margin = (float)((mg ? atof(mg) : 0.0) * P->cs);
     const char *bq = getenv("PCS_ICP_BATCH");
     A.batch = bq ? atoi(bq) : 16;
     if (A.batch < 1 || A.batch > 32) A.batch = 32;
@@ -2098,7 +2147,7 @@ static int launch_icp(cudaStream_t st, const pcs_trk_icp_t *P) {
     return set_error(PCS_ERR_BAD_ARG, "pcs_trk_icp: bad args");
   IcpB A = make_icp(P);
   long long cover = P->G > P->J ? P->G : P->J;
-  if ((P->max_iter + 2) * 2 > cover) cover = (P->max_iter + 2) * 2;
+  if ((P->max_iter + 2) * 3 > cover) cover = (P->max_iter + 2) * 3;
   if (P->J > kMaxInst) return set_error(PCS_ERR_BAD_ARG, "pcs_trk_icp: more than 1024 instances");
   PCS_LAUNCH(trk_icp_setup_kernel, blocks_for(cover, 256), 256, 0, st, A);
   PCS_LAUNCH(trk_icp_ranges_kernel, blocks_for(P->mv_cap > 0 ? P->mv_cap : 1, 256), 256, 0, st, A);

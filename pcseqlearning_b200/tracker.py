@@ -414,7 +414,7 @@ class TrackBatch:
                       mom=_z((G, 17), torch.float64, dev), Ti=_z((G, 12), torch.float64, dev), mu=_z((G, 6), torch.float64, dev),
                       l1_sum=_z((G, 2), torch.float64, dev), l1_n=_z(G, torch.float64, dev),
                       phase=_z(J, torch.int32, dev), cd=_z(J, torch.int32, dev), iters=_z(J, torch.int32, dev),
-                      itcnt=_z((80 + 2) * 2, torch.int32, dev), last=_z(J, torch.float64, dev),
+                      itcnt=_z((80 + 2) * 3, torch.int32, dev), last=_z(J, torch.float64, dev),
                       loss=_z(J, torch.float64, dev), match_cnt=_z(G, torch.int32, dev))
             _lib.check(L.pcs_trk_table_clear(s, _ptr(sc["mov_table"]), Hm, _ptr(sc["mov_ctr"])), "pcs_trk_table_clear")
             self.sc = sc
@@ -604,7 +604,7 @@ def register_pair(mov_fxyz, mov_comp, mov_stationary, ref_fxyz, ref_stationary, 
                       mom=_z((C, 17), torch.float64, dev), Ti=_z((C, 12), torch.float64, dev),
                       mu=_z((C, 6), torch.float64, dev), l1_sum=_z((C, 2), torch.float64, dev), l1_n=_z(C, torch.float64, dev),
                       phase=_z(1, torch.int32, dev), cd=_z(1, torch.int32, dev), iters=iters,
-                      itcnt=_z((int(max_iter) + 2) * 2, torch.int32, dev), last=_z(1, torch.float64, dev),
+                      itcnt=_z((int(max_iter) + 2) * 3, torch.int32, dev), last=_z(1, torch.float64, dev),
                       loss=_z(1, torch.float64, dev), match_cnt=_z(C, torch.int32, dev))
             _lib.check(L.pcs_trk_table_clear(s, _ptr(sc["mov_table"]), Hm, _ptr(sc["mov_ctr"])), "pcs_trk_table_clear")
             st = IcpStruct()
