@@ -120,6 +120,17 @@ int pcs_radius_search(pcs_stream_t s, const pcs_slot_t *table, int64_t H, const 
                       int32_t *const *uf_parents, const float *uf_r2, const int *uf_need_full, int n_uf,
                       const int32_t *skip_full_cnt, const uint32_t *occ, int64_t occ_bits);
 
+/* Self-query search with fused connected components, ONE THREAD per query, for the cluster-proposal passes
+ * (cluster_proposal.py:63-81 -> graph_utils.py:149-209 + :40-53; torch_hash_kernel.cu:224-409): every grid row is a
+ * query (taken in cell order), no lists are written, only nbr_cnt int32[n] = min(#accepted, K) and the unions of the
+ * query with its K nearest rows into the forests (same uf_* / skip_full_cnt semantics and the same candidate set,
+ * distance test and tie rule as pcs_radius_search, whose self-query + union-find mode it replaces).  Scalar radius. */
+int pcs_self_search_uf(pcs_stream_t s, const pcs_slot_t *table, int64_t H, const float *sorted_pts,
+                       const int32_t *sorted_idx, int64_t n, int seg_div, int n_seg, const float *seg_lo,
+                       const int64_t *seg_dims, const float *vs, const int *qmin, const int *qmax, float radius, int K,
+                       int32_t *nbr_cnt, int32_t *const *uf_parents, const float *uf_r2, const int *uf_need_full,
+                       int n_uf, const int32_t *skip_full_cnt, const uint32_t *occ, int64_t occ_bits);
+
 /* Exclusive scan int32 -> int64 with the grand total at out[n] (out has n+1 entries).
  * Replaces `cumsum(degree) - degree` (torch_hash_kernel.cu:534-538) without the two blocking .item(). */
 int pcs_exclusive_scan(pcs_stream_t s, const int32_t *in, int64_t n, int64_t *out, void *tmp, int64_t tmp_bytes);

@@ -35,6 +35,9 @@ _SIGNATURES = {
                                   c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
                                   c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                   c_void_p, c_void_p, c_int64]),
+    "pcs_self_search_uf": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p,
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_int, c_void_p, c_void_p, c_int64]),
     "pcs_exclusive_scan": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64]),
     "pcs_exclusive_scan_tmp_bytes": (c_int64, [c_int64]),
     "pcs_lists_to_edges": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p,

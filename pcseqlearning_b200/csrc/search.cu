@@ -262,6 +262,134 @@ radius_search_kernel(const pcs_slot_t *__restrict__ table, long long mask, const
   }
 }
 
+// ---- thread-per-query self search with fused union-find ("cell-coherent" variant) ------------------------------
+// The cluster-proposal passes need no neighbour lists, only (a) the union of every query with its K nearest points
+// within r and (b) min(count, K).  With the queries taken in cell order, the 32 lanes of a warp sit in a handful of
+// neighbouring cells, so ONE thread per query walks its 27 cells on its own: slot and row loads of neighbouring
+// lanes hit the same lines, nothing is exchanged between lanes, and the instruction count per query drops from
+// ~1400 warp instructions (one warp per query) to that many THREAD instructions.  The K-list lives in shared memory,
+// one column per thread ([K][threads]: conflict-free); while it is not full, candidates are appended, afterwards a
+// candidate replaces the current worst entry (largest (d2, index) key) and the worst is searched again -- the set
+// that remains is exactly the K smallest keys, the same set the warp kernel keeps.
+constexpr int kTqThreads = 128;
+
+__global__ void __launch_bounds__(kTqThreads, 6)
+self_search_uf_kernel(const pcs_slot_t *__restrict__ table, long long mask, const float4 *__restrict__ sorted_pts,
+                      const int *__restrict__ sorted_idx, SegGeom g, long long m, QueryRange qr, float r2, int K,
+                      int *nbr_cnt, UfTargets uf, const int *skip_full_cnt,  // may alias: no __restrict__
+                      const unsigned int *__restrict__ occ, int occ_shift) {
+  __shared__ float4 s_lo[PCS_MAX_SEGMENTS];
+  __shared__ long long s_dims[PCS_MAX_SEGMENTS * 4];
+  extern __shared__ unsigned long long s_klist[];  // [K][kTqThreads]
+  load_geom(g, s_lo, s_dims);
+  __syncthreads();
+  unsigned long long *list = s_klist + threadIdx.x;
+  const long long w = (long long)blockIdx.x * kTqThreads + threadIdx.x;
+  if (w >= m) return;
+  const long long q = (long long)sorted_idx[w];
+  if (skip_full_cnt && skip_full_cnt[q] >= K) return;
+  const float4 qp = sorted_pts[w];
+  const int seg = point_segment(qp.x, g.seg_div, g.n_seg);
+  const float4 lo = s_lo[seg];
+  const long long *dims = s_dims + seg * 4;
+  const float u0 = __fdiv_rn(__fsub_rn(qp.x, lo.x), g.vs[0]);
+  const float u1 = __fdiv_rn(__fsub_rn(qp.y, lo.y), g.vs[1]);
+  const float u2 = __fdiv_rn(__fsub_rn(qp.z, lo.z), g.vs[2]);
+  const float u3 = __fdiv_rn(__fsub_rn(qp.w, lo.w), g.vs[3]);
+  const float n0 = rintf(u0), n1 = rintf(u1), n2 = rintf(u2), n3 = rintf(u3);
+  const long long qc0 = (long long)n0 + 1, qc1 = (long long)n1 + 1, qc2 = (long long)n2 + 1, qc3 = (long long)n3 + 1;
+
+  int fill = 0, worst_pos = 0;
+  unsigned long long worst = 0ull;
+  float worst_d2 = __int_as_float(0x7f800000);  // +inf while the list is not full
+  for (int cell = 0; cell < qr.nc; ++cell) {
+    int t = cell;
+    const int o0 = t % qr.range[0] + qr.qmin[0];
+    t /= qr.range[0];
+    const int o1 = t % qr.range[1] + qr.qmin[1];
+    t /= qr.range[1];
+    const int o2 = t % qr.range[2] + qr.qmin[2];
+    t /= qr.range[2];
+    const int o3 = t % qr.range[3] + qr.qmin[3];
+    const long long c0 = qc0 + o0, c1 = qc1 + o1, c2 = qc2 + o2, c3 = qc3 + o3;
+    float dmin2 = 0.f;
+    const bool clamped = c0 < 0 || c0 > dims[0] || c1 < 0 || c1 > dims[1] || c2 < 0 || c2 > dims[2] || c3 < 0 ||
+                         c3 > dims[3];
+    if (!clamped) {
+      const float g1 = axis_gap(o1, u1 - n1, u1, g.vs[1]);
+      const float g2 = axis_gap(o2, u2 - n2, u2, g.vs[2]);
+      const float g3 = axis_gap(o3, u3 - n3, u3, g.vs[3]);
+      dmin2 = (g1 * g1 + g2 * g2 + g3 * g3) * 0.99999f;
+    }
+    if (dmin2 > fminf(r2, worst_d2)) continue;
+    const long long key = map2key4(c0, c1, c2, c3, dims) | ((long long)seg << PCS_SEG_SHIFT);
+    const unsigned int h = hash_key(key);
+    if (occ) {
+      const unsigned int b = h >> occ_shift;
+      if (!((__ldg(occ + (b >> 5)) >> (b & 31)) & 1u)) continue;
+    }
+    int start = 0, count = 0;
+    {
+      const int klo = (int)(unsigned int)key, khi = (int)(key >> 32);
+      unsigned int slot = h & (unsigned int)mask;
+      for (unsigned int probes = 0; probes <= (unsigned int)mask; ++probes) {
+        const int4 v = __ldg(reinterpret_cast<const int4 *>(table + slot));
+        if (v.x == klo && v.y == khi) {
+          start = v.z;
+          count = v.w;
+          break;
+        }
+        if ((v.x & v.y) == -1) break;
+        slot = (slot + 1) & (unsigned int)mask;
+      }
+    }
+    for (int j = 0; j < count; ++j) {
+      const float d2 = dist2_ref(__ldg(sorted_pts + start + j), qp);
+      if (!(d2 <= r2) || !(d2 <= worst_d2)) continue;
+      const unsigned long long key64 =
+          ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned int)__ldg(sorted_idx + start + j);
+      if (fill < K) {
+        list[fill * kTqThreads] = key64;
+        ++fill;
+        if (fill < K) continue;
+      } else {
+        if (!(key64 < worst)) continue;
+        list[worst_pos * kTqThreads] = key64;
+      }
+      // the list is full: (re)locate its largest key
+      worst = 0ull;
+      for (int i = 0; i < K; ++i) {
+        const unsigned long long v = list[i * kTqThreads];
+        if (v >= worst) {
+          worst = v;
+          worst_pos = i;
+        }
+      }
+      worst_d2 = __uint_as_float((unsigned int)(worst >> 32));
+    }
+  }
+  if (nbr_cnt) nbr_cnt[q] = fill;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    if (k >= uf.n) break;
+    if (uf.need_full[k] && fill < K) continue;
+    int *parent = uf.parent[k];
+    const float rk2 = uf.r2[k];
+    int rq = uf_find(parent, (int)q);
+    for (int i = 0; i < fill; ++i) {
+      const unsigned long long v = list[i * kTqThreads];
+      if (!(__uint_as_float((unsigned int)(v >> 32)) <= rk2)) continue;
+      const int idx = (int)(unsigned int)(v & 0xffffffffu);
+      if (idx == (int)q) continue;
+      const int ri = uf_find(parent, idx);
+      if (ri != rq) {
+        uf_unite(parent, rq, ri);
+        rq = uf_find(parent, (int)q);
+      }
+    }
+  }
+}
+
 // padded lists -> int64[E][2] rows (ref, query) grouped by ascending query
 __global__ void __launch_bounds__(256) lists_to_edges_kernel(const int *__restrict__ nbr_idx,
                                                              const float *__restrict__ nbr_d2,
@@ -346,6 +474,57 @@ int pcs_radius_search(pcs_stream_t s, const pcs_slot_t *table, int64_t H, const 
                (const float4 *)sorted_pts, sorted_idx, g, (const float4 *)queries, (long long)m, order, qr, radius,
                radius_scalar, K, nbr_idx, nbr_d2, nbr_cnt, uf, skip_full_cnt, occ, occ_shift);
   }
+  return 0;
+}
+
+int pcs_self_search_uf(pcs_stream_t s, const pcs_slot_t *table, int64_t H, const float *sorted_pts,
+                       const int32_t *sorted_idx, int64_t n, int seg_div, int n_seg, const float *seg_lo,
+                       const int64_t *seg_dims, const float *vs, const int *qmin, const int *qmax, float radius, int K,
+                       int32_t *nbr_cnt, int32_t *const *uf_parents, const float *uf_r2, const int *uf_need_full,
+                       int n_uf, const int32_t *skip_full_cnt, const uint32_t *occ, int64_t occ_bits) {
+  if (occ && (occ_bits < 32 || occ_bits > (1LL << 32) || (occ_bits & (occ_bits - 1))))
+    return set_error(PCS_ERR_BAD_ARG, "pcs_self_search_uf: occ_bits must be a power of two in [32, 2^32]");
+  int occ_shift = 0;
+  if (occ) {
+    int lg = 0;
+    while ((1LL << lg) < occ_bits) ++lg;
+    occ_shift = 32 - lg;
+  }
+  if (!table || H < 2 || H > (1LL << 31) || (H & (H - 1)) || K < 1 || K > PCS_MAX_K || n_seg < 1 ||
+      n_seg > PCS_MAX_SEGMENTS || !qmin || !qmax || ((uintptr_t)sorted_pts & 15) || n < 0 || n >= (1LL << 31) ||
+      (n > 0 && (!sorted_pts || !sorted_idx)))
+    return set_error(PCS_ERR_BAD_ARG, "pcs_self_search_uf: bad args (1 <= K <= 32, 16-byte aligned points)");
+  if (n_uf < 1 || n_uf > 3 || !uf_parents || !uf_r2 || !uf_need_full)
+    return set_error(PCS_ERR_BAD_ARG, "pcs_self_search_uf: 1 to 3 union-find targets");
+  UfTargets uf;
+  uf.n = n_uf;
+  for (int k = 0; k < 3; k++) {
+    uf.parent[k] = k < n_uf ? uf_parents[k] : nullptr;
+    uf.r2[k] = k < n_uf ? uf_r2[k] : 0.f;
+    uf.need_full[k] = k < n_uf ? uf_need_full[k] : 0;
+    if (k < n_uf && !uf.parent[k]) return set_error(PCS_ERR_BAD_ARG, "pcs_self_search_uf: null union-find forest");
+  }
+  if (n == 0) return 0;
+  QueryRange qr;
+  qr.nc = 1;
+  qr.append = qr.prefetch = 0;
+  for (int i = 0; i < 4; i++) {
+    qr.qmin[i] = qmin[i];
+    qr.range[i] = qmax[i] - qmin[i] + 1;
+    if (qr.range[i] < 1) return set_error(PCS_ERR_BAD_ARG, "pcs_self_search_uf: qmax < qmin");
+    qr.nc *= qr.range[i];
+  }
+  SegGeom g = make_geom(seg_lo, seg_dims, vs, seg_div, n_seg);
+  const size_t smem = (size_t)K * kTqThreads * sizeof(unsigned long long);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(self_search_uf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * kTqThreads * 8);
+    attr_set = true;
+  }
+  const float r = radius;
+  PCS_LAUNCH(self_search_uf_kernel, (unsigned)((n + kTqThreads - 1) / kTqThreads), kTqThreads, smem, as_stream(s),
+             table, (long long)(H - 1), (const float4 *)sorted_pts, sorted_idx, g, (long long)n, qr, r * r, K,
+             nbr_cnt, uf, skip_full_cnt, occ, occ_shift);
   return 0;
 }
 

@@ -2303,11 +2303,28 @@ __global__ void __launch_bounds__(256) trk_gsearch_kernel(PGrid g, const float4 
   const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   const int total = seg_off[nseg];
-  for (long long w = warp_id; w < total; w += nwarps) {
-    const int sg = seg_of_item(seg_off, nseg, (int)w);
-    const float4 q = queries[seg_qstart[sg] + ((int)w - seg_off[sg])];
-    const int r = nn_search(g, true, seg_group[sg], q.y, q.z, q.w, 0.f, r2, 0u, lane);
-    if (lane == 0) out[w] = r;
+  // 32 consecutive queries per warp (coalesced loads and stores, one segment lookup per lane), searched one by one
+  for (long long base = warp_id * 32; base < total; base += nwarps * 32) {
+    const long long w = base + lane;
+    bool need = w < total;
+    int grp = 0;
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (need) {
+      const int sg = seg_of_item(seg_off, nseg, (int)w);
+      q = queries[seg_qstart[sg] + ((int)w - seg_off[sg])];
+      grp = seg_group[sg];
+    }
+    int res = -1;
+    unsigned int todo = __ballot_sync(kAll, need);
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int sgrp = __shfl_sync(kAll, grp, src);
+      const float sx = __shfl_sync(kAll, q.y, src), sy = __shfl_sync(kAll, q.z, src), sz = __shfl_sync(kAll, q.w, src);
+      const int r = nn_search(g, true, sgrp, sx, sy, sz, 0.f, r2, 0u, lane);
+      if (lane == src) res = r;
+    }
+    if (w < total) out[w] = res;
   }
 }
 

@@ -14,6 +14,9 @@ from . import _lib
 PCS_MAX_K = 32
 PCS_MAX_SEGMENTS = 64
 GRID_SORTED = int(os.environ.get("PCS_GRID_SORTED", "0"))  # staged: key-ordered cell ranges in the proposal grids
+SEARCH_THREADS = int(os.environ.get("PCS_SEARCH_THREADS", "0"))  # 1: thread-per-query kernel for the proposal passes
+# (measured, 198 frames: fine / mid / coarse pass 8.2 / 13.6 / 4.4 ms vs 7.8 / 9.4 / 1.6 ms for the warp kernel; with
+# key-ordered cells 5.4 / 12.0 / 3.0 ms but + 0.55 ms per grid build -- serial dependent loads per thread: off)
 OCC_BITS_PER_SLOT = int(os.environ.get("PCS_OCC_BITS_PER_SLOT", "16"))  # 0 disables the occupancy bitmap
 
 # Optional per-kernel CUDA-event log (bench.py's roofline leg): name -> list of (start, end, meta)
@@ -202,6 +205,16 @@ class CellGrid:
         uf_r2 = (ctypes.c_float * 3)(*[float(np.float32(t[1]) * np.float32(t[1])) if np.isfinite(t[1]) else 3.0e38
                                        for t in targets] + [0.0] * (3 - n_uf))
         uf_full = (ctypes.c_int * 3)(*[int(bool(t[2])) for t in targets] + [0] * (3 - n_uf))
+        if (query is None and not want_lists and n_uf >= 1 and rad_t is None and order is None and SEARCH_THREADS):
+            # cluster-proposal passes: thread-per-query kernel (no lists, unions + counts only)
+            with torch.cuda.device(dev), _timed("radius_search", n_ref=self.n, n_query=m, K=int(K), lists=False,
+                                                fused_uf=n_uf, threads=1):
+                _lib.check(_lib.lib().pcs_self_search_uf(
+                    _stream(), _ptr(self.table), self.H, _ptr(self.sorted_pts), _ptr(self.sorted_idx), self.n,
+                    self.seg_div, self.n_seg, _ptr(self.seg_lo), _ptr(self.seg_dims), _f4(self.vs), _i4(qmin), _i4(qmax),
+                    rad_s, int(K), _ptr(nbr_cnt), uf_ptrs, uf_r2, uf_full, n_uf, _ptr(skip_full_cnt), _ptr(self.occ),
+                    self.occ_bits), "pcs_self_search_uf")
+            return None, nbr_cnt, None
         with torch.cuda.device(dev), _timed("radius_search", n_ref=self.n, n_query=m, K=int(K), lists=bool(want_lists),
                                             fused_uf=n_uf):
             _lib.check(_lib.lib().pcs_radius_search(

@@ -119,6 +119,39 @@ def smooth_velo(_comp_velos, comp_center_diffs, frame_id, next_frame_id, weight0
     return velos.data
 
 
+class _stage_profile:
+    """Developer aid: PCS_PROFILE_STAGE=<stage> prints the torch ops of that tracker stage by device time and shapes."""
+
+    def __init__(self, name):
+        self.on = os.environ.get("PCS_PROFILE_STAGE") == name
+        self.name = name
+
+    def __enter__(self):
+        if self.on:
+            from torch.profiler import ProfilerActivity, profile
+            torch.cuda.synchronize()
+            self.prof = profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True)
+            self.prof.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.on:
+            torch.cuda.synchronize()
+            self.prof.__exit__(*exc)
+            rows = []
+            for ev in self.prof.key_averages(group_by_input_shape=True):
+                t = getattr(ev, "self_device_time_total", None)
+                if t is None:
+                    t = getattr(ev, "self_cuda_time_total", 0.0)
+                if t > 0:
+                    rows.append((t, ev.count, ev.key, str(ev.input_shapes)[:110]))
+            rows.sort(reverse=True)
+            print(f"[stage profile: {self.name}] total {sum(r[0] for r in rows) / 1e3:.1f} ms device", flush=True)
+            for t, n, key, shp in rows[:28]:
+                print(f"  {t / 1e3:7.2f} ms n={n:4d} {key[:48]:48s} {shp}", flush=True)
+        return False
+
+
 class ClusterTracking(nn.Module):
     def __init__(self, model_cfg, runtime_cfg):
         super().__init__()
@@ -395,7 +428,7 @@ class ClusterTracking(nn.Module):
         # ---- all above-ground points, grouped by frame --------------------------------------------------------
         a_frame = all_points.frame.reshape(-1).long()
         a_order = torch.argsort(a_frame, stable=True)
-        a_sorted = all_points.fxyz[a_order].contiguous()
+        a_sorted = ops.gather_rows(all_points.fxyz.contiguous(), a_order)  # (torch's row gather: 1 block per row)
         a_off = torch.zeros(F + 1, dtype=torch.int64, device=dev)
         a_off[1:] = torch.bincount(a_frame, minlength=F).cumsum(0)
         a_off_h = a_off.tolist()  # host sync
@@ -447,15 +480,16 @@ class ClusterTracking(nn.Module):
         i_all = w - seg_off_t[sg]
         srow = seg_qstart_t.long()[sg] + i_all  # row among the frame-sorted all_points
         gs = gs_ext[e]
-        ref_xyz = a_sorted[srow]
+        ref_xyz = ops.gather_rows(a_sorted, srow)
         dz = fl.fxyz[e, 3] - ref_xyz[:, 3]
         ok = (dz < 0.5) & (dz > -0.05)
         ok &= (ref_xyz[:, 1:3] - ctr[gs]).norm(p=2, dim=-1) < diam[gs] + 0.05  # :365-370
+        ok = ok.nonzero().reshape(-1)
         e, sg, i_all, srow, gs = e[ok], sg[ok], i_all[ok], srow[ok], gs[ok]
         rows = a_order[srow]  # rows of all_points
         inst_k = fl.inst[e]
         inst_bounds = torch.searchsorted(inst_k, torch.arange(J + 1, device=dev)).tolist()  # host sync
-        full = EasyDict(dict(fxyz=ref_xyz[ok], component=fl.component[e], frame_indices=i_all,
+        full = EasyDict(dict(fxyz=ops.gather_rows(ref_xyz, ok), component=fl.component[e], frame_indices=i_all,
                              original_indices=rows.reshape(-1, 1), moving=fl.moving[e]))
         for key in ("segmentation_label", "instance_label"):
             if f"full_{key}" in all_points:
@@ -578,15 +612,18 @@ class ClusterTracking(nn.Module):
                 seq_dict["tracking_results"], seq_dict["tracking_boxes"] = {}, seq_boxes
                 shard.all_reduce_max(seq_boxes.best_iou)
                 return seq_dict
-            tb = TrackBatch(seq_points.fxyz, seq_points.frame, comps, self.model_cfg, num_frames=num_frames,
-                            anchors=anchors)
+            with _stage_profile("setup"):
+                tb = TrackBatch(seq_points.fxyz, seq_points.frame, comps, self.model_cfg, num_frames=num_frames,
+                                anchors=anchors)
             mark("setup")
             tb.run()
             mark("run")
-            per_inst = tb.results(seg_label=seq_points.get("segmentation_label"))
-            tb.check()
+            with _stage_profile("results"):
+                per_inst = tb.results(seg_label=seq_points.get("segmentation_label"))
+                tb.check()
             mark("results")
-            full = self.extract_traces_batched(tb, all_points, seq_boxes)
+            with _stage_profile("extract_traces"):
+                full = self.extract_traces_batched(tb, all_points, seq_boxes)
             mark("extract_traces")
             lazy = self.model_cfg.get("LAZY_TRANSFORMS", False) and not save
             for ki, comp_key in enumerate(self.component_keys):

@@ -87,6 +87,27 @@ def _fill(struct, tensors, **kw):
             setattr(struct, k, v)
 
 
+def _rows(src, idx):
+    """src[idx] for point rows: torch's indexing kernel handles one 16-byte row per thread BLOCK (4 ms for 8 M rows);
+    pcs_gather_rows moves them at memory speed."""
+    from .ops import gather_rows
+    return gather_rows(src.contiguous(), idx)
+
+
+def _seg_minmax(values, ids, n_groups, empty_min, empty_max):
+    """(min, max) int64[n_groups] of integer `values` per group (warp-aggregated kernel: ids are mostly sorted; the
+    torch scatter_reduce serialises on the few hot bins).  Exact for |values| < 2^24; empty groups get the defaults."""
+    from .ops import group_minmax
+    if values.numel() == 0 or int(n_groups) < 1:
+        return (torch.full((int(n_groups),), empty_min, dtype=torch.int64, device=values.device),
+                torch.full((int(n_groups),), empty_max, dtype=torch.int64, device=values.device))
+    mn, mx = group_minmax(values.float().contiguous(), ids, n_groups)
+    cnt = torch.bincount(ids, minlength=n_groups)
+    has = cnt > 0
+    return (torch.where(has, mn.round().long(), torch.full_like(cnt, empty_min)),
+            torch.where(has, mx.round().long(), torch.full_like(cnt, empty_max)))
+
+
 def _z(n, dtype, dev):
     return torch.zeros(n, dtype=dtype, device=dev)
 
@@ -170,7 +191,7 @@ class TrackBatch:
             frame_off[1:] = fcnt.cumsum(0)
             off_h = frame_off.tolist()  # host sync: sizes of everything below
             self.order, self.frame_off_h = order, off_h
-            seq_sorted = fxyz[order].contiguous()
+            seq_sorted = _rows(fxyz, order)
             frame_sorted = frame[order].int().contiguous()
             pos_in_sorted = torch.empty(N, dtype=torch.int64, device=dev)
             pos_in_sorted[order] = torch.arange(N, device=dev)
@@ -207,8 +228,11 @@ class TrackBatch:
                 cframe = torch.zeros(Ck, dtype=torch.int64, device=dev).scatter_(0, c, frame)
                 valid = (deg > 0) & (diam < STATIONARY_DIAMETER)
                 statbits |= ((diam > STATIONARY_DIAMETER)[c].to(torch.uint8) << ki)
-                fminc = torch.full((F,), Ck, dtype=torch.int64, device=dev).scatter_reduce_(0, frame, c, "amin")
-                fmaxc = torch.full((F,), -1, dtype=torch.int64, device=dev).scatter_reduce_(0, frame, c, "amax")
+                if Ck < (1 << 24):
+                    fminc, fmaxc = _seg_minmax(c, frame, F, Ck, -1)
+                else:
+                    fminc = torch.full((F,), Ck, dtype=torch.int64, device=dev).scatter_reduce_(0, frame, c, "amin")
+                    fmaxc = torch.full((F,), -1, dtype=torch.int64, device=dev).scatter_reduce_(0, frame, c, "amax")
                 # non-empty components of the anchor frames, grouped by anchor (instance), ascending id inside
                 sel = ((deg > 0) & (anchor_index[cframe] >= 0)).nonzero().reshape(-1)
                 ai = anchor_index[cframe[sel]]
@@ -253,7 +277,7 @@ class TrackBatch:
             m_stat = torch.cat(m_stat).to(torch.uint8).contiguous()
             M = int(m_rows.shape[0])
             self.M = M
-            mp0 = fxyz[m_rows].contiguous()
+            mp0 = _rows(fxyz, m_rows)
             self.m_frow = (pos_in_sorted[m_rows] - frame_off[frame[m_rows]]).int().contiguous()
             inst_anchor = torch.tensor(anchors * nK, dtype=torch.int32, device=dev)
             inst_key = torch.arange(nK, device=dev).repeat_interleave(A).int()
@@ -297,8 +321,8 @@ class TrackBatch:
                 bits = vp[:, 0].contiguous().view(torch.int32)
                 sel_pts, sel_grp = [], []
                 for ki in range(nK):
-                    ns = ((bits >> ki) & 1) == 0
-                    sel_pts.append(vp[ns])
+                    ns = (((bits >> ki) & 1) == 0).nonzero().reshape(-1)
+                    sel_pts.append(_rows(vp, ns))
                     sel_grp.append(vf[ns] + ki * F)
                 sel_pts.append(vp)
                 sel_grp.append(vf + nK * F)
@@ -315,7 +339,7 @@ class TrackBatch:
                 perm = torch.sort(pos_key)[1]
                 ks, o2 = torch.sort(keys[perm], stable=True)
                 perm = perm[o2]
-                rv = cat_pts[perm].contiguous()
+                rv = _rows(cat_pts, perm)
                 rv_grp = cat_grp[perm]
                 uk, cnt = torch.unique_consecutive(ks, return_counts=True)
                 starts = (cnt.cumsum(0) - cnt).int().contiguous()
@@ -493,9 +517,12 @@ class TrackBatch:
         self._flat = EasyDict(dict(gid=gid, rows=rows, frame_rows=i_in, frame=f_of,
                                    inst=torch.div(slot, REL, rounding_mode="floor"),
                                    component=self.g_local[gid], moving=t["g_moving"].bool()[gid],
-                                   fxyz=self.fxyz[rows]))
+                                   fxyz=_rows(self.fxyz, rows)))
         self._flat["slot_bounds"] = slot_bounds
-        cmax = torch.full((J,), -1, dtype=torch.long, device=dev).scatter_reduce_(0, self._flat.inst, self._flat.component, "amax")
+        if self.g_local.numel() and int(self.g_local.max()) < (1 << 24):
+            cmax = _seg_minmax(self._flat.component, self._flat.inst, J, 0, -1)[1]
+        else:
+            cmax = torch.full((J,), -1, dtype=torch.long, device=dev).scatter_reduce_(0, self._flat.inst, self._flat.component, "amax")
         self.flat_cmax = cmax.tolist()
         return self._flat
 

@@ -191,6 +191,41 @@ def test_multi_radius_fused_equals_separate_searches(golden_dir):
         assert torch.equal(lab, want), r
 
 
+@pytest.mark.parametrize("K", [2, 8, 32])
+@pytest.mark.parametrize("sorted_cells", [False, True])
+def test_thread_search_equals_warp_search(K, sorted_cells):
+    """The thread-per-query proposal kernel (pcs_self_search_uf) against the warp-per-query kernel on the same grid:
+    identical counts min(#within r, K) and identical components, on a cloud dense enough that most lists overflow
+    (replacement path of the shared-memory K-list) and through the skip_full_cnt cascade."""
+    from pcseqlearning_b200 import ops
+    gen = torch.Generator(device="cuda").manual_seed(5 + K)
+    n = 300_000
+    pts = torch.rand(n, 4, generator=gen, device="cuda") * torch.tensor([1.0, 30.0, 30.0, 2.0], device="cuda")
+    pts[:, 0] = torch.randint(0, 25, (n,), generator=gen, device="cuda").float()
+    pts[: n // 10, 1:] *= 0.1  # a very dense corner: hundreds of candidates per query
+    n_seg = 3
+    out = {}
+    for mode in (1, 0):
+        ops.SEARCH_THREADS = mode
+        try:
+            cnt = None
+            parents = []
+            for r in (0.2, 0.5):
+                grid = ops.CellGrid(pts, ops.radius_voxel_size(r), seg_div=10, n_seg=n_seg, sorted_cells=sorted_cells)
+                parent = ops.uf_new(n, pts.device) if not parents else parents[-1].clone()
+                _, cnt, _ = grid.search(None, K, r, uf_parent=parent, want_lists=False, skip_full_cnt=cnt, cnt_out=cnt)
+                grid.check()
+                parents.append(parent)
+            seg_of = ops.point_segments(pts, 10, n_seg)
+            out[mode] = (cnt.clone(), [ops.uf_labels(p_, seg_of, n_seg)[1] for p_ in parents])
+        finally:
+            ops.SEARCH_THREADS = 0
+    assert torch.equal(out[1][0], out[0][0])
+    assert int((out[1][0] >= K).sum()) > n // 20  # the overflow path was exercised
+    for a, b in zip(out[1][1], out[0][1]):
+        assert torch.equal(a, b)
+
+
 def test_compact_table_overflow_falls_back():
     """A point set with one point per cell overflows the compact table; the grid must be rebuilt, not corrupted."""
     from oracle import cpu_ops as oracle
