@@ -1122,6 +1122,10 @@ __global__ void __launch_bounds__(kTrkThreads, kMinBlocks) trk_icp_kernel(IcpB A
         const int r = sf ? nn_search_rings(A.ref, false, A.ref_group[sj], sx, sy, sz, A.acc0, A.r2, ss, lane, A.rings, sk, olb, mg)
                          : nn_search_rings(A.mov, true, sj, sx, sy, sz, A.acc0, A.r2, 0u, lane, A.rings, sk, olb, mg);
         if (lane == src) {
+          if (A.prof) {  // what the searches were good for: [208] same neighbour as before, [209] changed, [210] no previous
+            const int slot = it == 0 ? 211 : (prev < 0 ? 210 : (r == prev ? 208 : 209));
+            atomicAdd((unsigned long long *)A.prof + slot, 1ull);
+          }
           res = r;
           sec = sqrtf(fmaxf(olb2 - A.acc0, 0.f)) * 0.9999f;
         }

@@ -654,7 +654,8 @@ class ClusterTracking(nn.Module):
                     pr = pr.tolist()
                     print(f"[icp level {lv}] launches {pr[9]} iterations {pr[8]} thread-path {pr[10]} warp-path {pr[11]} "
                           f"unmatched {pr[12]} cached {pr[15]} " +
-                          ", ".join(f"{n} {pr[i] / 1e6:.1f} ms" for i, n in enumerate(names)), flush=True)
+                          ", ".join(f"{n} {pr[i] / 1e6:.1f} ms" for i, n in enumerate(names)) +
+                          f" | searches: same {pr[208]} changed {pr[209]} no-prev {pr[210]} first-it {pr[211]}", flush=True)
                     if os.environ.get("PCS_TRACK_TIMING") == "2":
                         print("   per-iteration search ms (summed over launches): " +
                               " ".join(f"{pr[16 + i] / 1e6:.1f}" for i in range(80)))
