@@ -5,7 +5,7 @@ persistent kernel (ops.register_icp); the small segmented reductions used by the
 index ops on a few thousand components."""
 import torch
 
-from .. import ops
+from .. import _lib, ops
 from ..utils.scatter import scatter_count, scatter_mean, scatter_sum
 
 
@@ -44,12 +44,18 @@ def register_to_next_frame(graph, moving, ref, num_components, angle_regularizer
     graph: the level's RadiusGraph (only its radius is used; qmin/qmax are left untouched).
     Returns (moving with fxyz moved, T f64[C,4,4], l1_component_error f64[C], comp_edge_ratio f32[C]).
     """
+    if int(getattr(graph, "max_num_neighbors", 1)) != 1:
+        raise _lib.PcsError("register_to_next_frame: the registration graph must have MAX_NUM_NEIGHBORS == 1 "
+                            "(the ICP kernel keeps the single nearest neighbour, like the reference's config)")
     if frame_offset is None:
         frame_offset = int((ref.frame.reshape(-1)[0] - moving.frame.reshape(-1)[0]).long().item())
     moved, T, l1, ratio, info = ops.register_icp(
         moving.fxyz, moving.component, moving.stationary, ref.fxyz, ref.stationary, num_components,
         float(graph.radius), frame_offset, angle_regularizer=float(angle_regularizer), max_iter=int(max_iter),
         stopping_delta=float(stopping_delta))
-    moving.fxyz = moved
+    if moving.fxyz.shape == moved.shape and moving.fxyz.dtype == moved.dtype:
+        moving.fxyz.copy_(moved)  # the reference updates the tensor in place (:179): holders of it see the move
+    else:
+        moving.fxyz = moved
     moving["icp_info"] = info
     return moving, T, l1, ratio
