@@ -788,7 +788,42 @@ struct IcpB {
   long long *prof;  // optional [16]: nanoseconds per phase (B, C, D, E, F, G, H, tail), [8] iterations, [9] launches
 };
 
-// same solve as icp.cu (kept there for the single-instance entry point)
+// Jacobi rotation with one reciprocal square root instead of a square root and a division: the solve of an ICP
+// iteration is a pure latency chain (one thread per component, every other warp waits at the barrier), and the fp64
+// divisions and square roots are most of it.
+#define TRK_JACOBI_ROT(app, aqq, apq, arp, arq, v0p, v0q, v1p, v1q, v2p, v2q)          \
+  if ((apq) != 0.0) {                                                                  \
+    const double theta = ((aqq) - (app)) / (2.0 * (apq));                              \
+    const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0)); \
+    const double c = rsqrt(t * t + 1.0), sn = t * c;                                   \
+    (app) -= t * (apq);                                                                \
+    (aqq) += t * (apq);                                                                \
+    (apq) = 0.0;                                                                       \
+    { const double x = (arp), y = (arq); (arp) = c * x - sn * y; (arq) = sn * x + c * y; } \
+    { const double x = (v0p), y = (v0q); (v0p) = c * x - sn * y; (v0q) = sn * x + c * y; } \
+    { const double x = (v1p), y = (v1q); (v1p) = c * x - sn * y; (v1q) = sn * x + c * y; } \
+    { const double x = (v2p), y = (v2q); (v2p) = c * x - sn * y; (v2q) = sn * x + c * y; } \
+  }
+
+__device__ __forceinline__ Eig3 trk_jacobi_eig3(double a00, double a01, double a02, double a11, double a12, double a22) {
+  Eig3 e;
+  e.v00 = e.v11 = e.v22 = 1.0;
+  e.v01 = e.v02 = e.v10 = e.v12 = e.v20 = e.v21 = 0.0;
+  for (int sweep = 0; sweep < 30; sweep++) {
+    const double off = fabs(a01) + fabs(a02) + fabs(a12);
+    const double diag = fabs(a00) + fabs(a11) + fabs(a22);
+    // off-diagonal mass below 1e-16 of the diagonal: the next sweep would square it (quadratic convergence)
+    if (off == 0.0 || off <= 1e-16 * diag) break;
+    TRK_JACOBI_ROT(a00, a11, a01, a02, a12, e.v00, e.v01, e.v10, e.v11, e.v20, e.v21)
+    TRK_JACOBI_ROT(a00, a22, a02, a01, a12, e.v00, e.v02, e.v10, e.v12, e.v20, e.v22)
+    TRK_JACOBI_ROT(a11, a22, a12, a01, a02, e.v01, e.v02, e.v11, e.v12, e.v21, e.v22)
+  }
+  e.d0 = a00;
+  e.d1 = a11;
+  e.d2 = a22;
+  return e;
+}
+
 __device__ void kabsch_rotation_b(const double A[9], double R[9]) {
   double b00 = 0, b01 = 0, b02 = 0, b11 = 0, b12 = 0, b22 = 0;
 #pragma unroll
@@ -801,7 +836,7 @@ __device__ void kabsch_rotation_b(const double A[9], double R[9]) {
     b12 += y * z;
     b22 += z * z;
   }
-  const Eig3 e = jacobi_eig3(b00, b01, b02, b11, b12, b22);
+  const Eig3 e = trk_jacobi_eig3(b00, b01, b02, b11, b12, b22);
   double ev[3] = {e.d0, e.d1, e.d2};
   double V[3][3] = {{e.v00, e.v01, e.v02}, {e.v10, e.v11, e.v12}, {e.v20, e.v21, e.v22}};
   int i0 = 0, i1 = 1, i2 = 2;
@@ -812,13 +847,14 @@ __device__ void kabsch_rotation_b(const double A[9], double R[9]) {
   double Vs[3][3], U[3][3];
 #pragma unroll
   for (int j = 0; j < 3; j++) {
-    const double sv = sqrt(fmax(ev[idx[j]], 0.0));
+    const double sv2 = fmax(ev[idx[j]], 0.0);
+    const double inv_sv = sv2 > 1e-300 ? rsqrt(sv2) : 0.0;  // 1 / singular value (sv > 1e-150 ... the guard of before)
 #pragma unroll
     for (int i = 0; i < 3; i++) Vs[i][j] = V[i][idx[j]];
 #pragma unroll
     for (int i = 0; i < 3; i++) {
       const double av = A[i * 3 + 0] * Vs[0][j] + A[i * 3 + 1] * Vs[1][j] + A[i * 3 + 2] * Vs[2][j];
-      U[i][j] = sv > 1e-300 ? av / sv : 0.0;
+      U[i][j] = av * inv_sv;
     }
   }
   if (!(ev[i2] > 1e-24 * fmax(ev[i0], 1e-300))) {
@@ -2332,6 +2368,23 @@ __global__ void __launch_bounds__(256) trk_gsearch_kernel(PGrid g, const float4 
   }
 }
 
+// One THREAD per query: most queries of the trace extraction have no stored point anywhere near them (27 empty lookups,
+// nothing to sweep), which a whole warp per query only makes 32 times more expensive.
+__global__ void __launch_bounds__(256) trk_gsearch_thread_kernel(PGrid g, const float4 *__restrict__ queries,
+                                                                 const int *__restrict__ seg_qstart,
+                                                                 const int *__restrict__ seg_off,
+                                                                 const int *__restrict__ seg_group, int nseg, float r2,
+                                                                 int *__restrict__ out) {
+  const int total = seg_off[nseg];
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += stride) {
+    const int sg = seg_of_item(seg_off, nseg, (int)w);
+    const float4 q = queries[seg_qstart[sg] + ((int)w - seg_off[sg])];
+    const unsigned long long k = nn_search_thread(g, true, seg_group[sg], q.y, q.z, q.w, 0.f, r2, 0u);
+    out[w] = k == ~0ull ? -1 : (int)(unsigned int)(k & 0xffffffffu);
+  }
+}
+
 }  // namespace pcs
 
 extern "C" {
@@ -2364,8 +2417,17 @@ int pcs_trk_group_nn(pcs_stream_t s, const pcs_slot_t *table, int64_t H, const f
     return set_error(PCS_ERR_BAD_ARG, "pcs_trk_group_nn: bad args");
   if (nseg == 0) return 0;
   PGrid g = make_pgrid((void *)table, H, (void *)sorted, (void *)sidx, nullptr, nullptr, lo, cs);
-  PCS_LAUNCH(trk_gsearch_kernel, 148 * 8, 256, 0, as_stream(s), g, (const float4 *)queries, seg_qstart, seg_off,
-             seg_group, nseg, radius * radius, out);
+  static int mode = -1;
+  if (mode < 0) {
+    const char *e = getenv("PCS_GSEARCH_WARP");
+    mode = (e && atoi(e)) ? 1 : 0;
+  }
+  if (mode == 1)
+    PCS_LAUNCH(trk_gsearch_kernel, 148 * 8, 256, 0, as_stream(s), g, (const float4 *)queries, seg_qstart, seg_off,
+               seg_group, nseg, radius * radius, out);
+  else
+    PCS_LAUNCH(trk_gsearch_thread_kernel, 148 * 8, 256, 0, as_stream(s), g, (const float4 *)queries, seg_qstart,
+               seg_off, seg_group, nseg, radius * radius, out);
   return 0;
 }
 
