@@ -955,8 +955,8 @@ __device__ __forceinline__ long long gtime() {
 
 constexpr int kMaxInst = 1024;
 
-template <int kMinBlocks>
-__global__ void __launch_bounds__(kTrkThreads, kMinBlocks) trk_icp_kernel(IcpB A) {
+template <int kMinBlocks, int kThreads = kTrkThreads>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) trk_icp_kernel(IcpB A) {
   __shared__ int s_aoff[kMaxInst + 1];
   cg::grid_group grid = cg::this_grid();
   long long t_prev = gtime();
@@ -1023,25 +1023,38 @@ __global__ void __launch_bounds__(kTrkThreads, kMinBlocks) trk_icp_kernel(IcpB A
     // settled by its own thread (27 fine cells, bound = that distance: exact); the others -- first iteration, lost
     // or far neighbours -- are searched by the whole warp, one after the other, over the 5x5x5 block.
     // active work items of this iteration: [forward voxels | backward reference voxels] of every running instance
-    if (threadIdx.x == 0) {
-      int o = 0;
-      for (int jj = 0; jj < A.J; jj++) {
-        s_aoff[jj] = o;
-        if (A.phase[jj] == PH_RUN) o += (A.mvend[jj] - A.mvbeg[jj]) + (A.boff[jj + 1] - A.boff[jj]);
+    // (every thread loads one instance -- the barrier before this phase invalidated L1, a serial loop of one thread
+    // over the instances would be a chain of L2 round trips with the rest of the CTA waiting)
+    for (int jj = threadIdx.x; jj < A.J; jj += blockDim.x) {
+      int nf = 0, nb = 0;
+      if (A.phase[jj] == PH_RUN) {
+        nf = A.mvend[jj] - A.mvbeg[jj];
+        nb = A.boff[jj + 1] - A.boff[jj];
+        if (A.prof && blockIdx.x == 0) {
+          atomicAdd((unsigned long long *)A.prof + 13, (unsigned long long)nf);
+          atomicAdd((unsigned long long *)A.prof + 14, (unsigned long long)nb);
+        }
       }
-      s_aoff[A.J] = o;
+      s_aoff[jj + 1] = nf + nb;
+    }
+    if (threadIdx.x == 0) s_aoff[0] = 0;
+    __syncthreads();
+    if (threadIdx.x < 32) {  // in-place inclusive scan of s_aoff[1 .. J] by the first warp
+      int carry = 0;
+      for (int base = 1; base <= A.J; base += 32) {
+        const int i = base + lane;
+        int v = i <= A.J ? s_aoff[i] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(kAll, v, o);
+          if (lane >= o) v += t;
+        }
+        v += carry;
+        if (i <= A.J) s_aoff[i] = v;
+        carry = __shfl_sync(kAll, v, 31);
+      }
     }
     __syncthreads();
-    if (A.prof && tid == 0) {
-      long long nf = 0, nb = 0;
-      for (int jj = 0; jj < A.J; jj++)
-        if (A.phase[jj] == PH_RUN) {
-          nf += A.mvend[jj] - A.mvbeg[jj];
-          nb += A.boff[jj + 1] - A.boff[jj];
-        }
-      A.prof[13] += nf;
-      A.prof[14] += nb;
-    }
     const int n_active = s_aoff[A.J];
     // work items per warp batch (<= 32): the items of a batch are searched one after the other by the warp, so in
     // the long tail of an ICP (few instances still iterating) smaller batches spread the latency chains over all warps
@@ -1224,7 +1237,9 @@ __global__ void __launch_bounds__(kTrkThreads, kMinBlocks) trk_icp_kernel(IcpB A
     if (A.prof && tid == 0 && it < 96) A.prof[16 + it] += gtime() - t_prev;
     ICP_PROF(3)
     // ---- F: per-component solve (thread per component) + instance loss ; the moving grid is released ----------
-    for (long long c0 = tid - lane; c0 < A.G; c0 += nth) {
+    // consecutive groups of 32 components go to different CTAs: the solve is a long fp64 latency chain per thread and
+    // there are only a few hundred warps of it, which should not queue up on the first SMs
+    for (long long c0 = ((long long)(threadIdx.x >> 5) * gridDim.x + blockIdx.x) * 32; c0 < A.G; c0 += nwarps * 32) {
       const long long c = c0 + lane;
       double loss_part = 0.0;
       int j = -1;
@@ -2196,8 +2211,24 @@ static int launch_icp(cudaStream_t st, const pcs_trk_icp_t *P) {
     const char *o = getenv("PCS_ICP_OCC");
     occ = o ? atoi(o) : 4;
   }
+  // CTA size: the same 32 warps per SM as 4 x 256, 2 x 512 or 1 x 1024 threads -- fewer, larger CTAs make the grid-wide
+  // barrier (one atomic + one spinning thread per CTA) cheaper; PCS_ICP_BLOCK selects
+  static int block = -1;
+  if (block < 0) {
+    const char *b = getenv("PCS_ICP_BLOCK");
+    block = b ? atoi(b) : 1024;  // measured (198 frames): tracker 526 / 512 / 487 ms at 256 / 512 / 1024
+    if (block != 512 && block != 256) block = 1024;
+  }
   const void *kern = occ >= 4 ? (const void *)trk_icp_kernel<4> : (occ == 3 ? (const void *)trk_icp_kernel<3> : (const void *)trk_icp_kernel<2>);
-  const int blocks = coop_grid(kern, kTrkThreads, 1LL << 40, occ >= 4 ? 4 : (occ == 3 ? 3 : 2));
+  int per_sm = occ >= 4 ? 4 : (occ == 3 ? 3 : 2);
+  if (block == 512) {
+    kern = (const void *)trk_icp_kernel<2, 512>;
+    per_sm = 2;
+  } else if (block == 1024) {
+    kern = (const void *)trk_icp_kernel<1, 1024>;
+    per_sm = 1;
+  }
+  const int blocks = coop_grid(kern, block, 1LL << 40, per_sm);
   void *args[] = {&A};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   if (g_icp_timing) {
@@ -2205,7 +2236,7 @@ static int launch_icp(cudaStream_t st, const pcs_trk_icp_t *P) {
     cudaEventCreate(&ev1);
     cudaEventRecord(ev0, st);
   }
-  cudaError_t e = cudaLaunchCooperativeKernel(kern, dim3((unsigned)blocks), dim3(kTrkThreads), args, 0, st);
+  cudaError_t e = cudaLaunchCooperativeKernel(kern, dim3((unsigned)blocks), dim3((unsigned)block), args, 0, st);
   if (g_icp_timing) {
     cudaEventRecord(ev1, st);
     g_icp_events.emplace_back(ev0, ev1);
