@@ -1887,6 +1887,24 @@ __global__ void __launch_bounds__(256) trk_extract_kernel(Trk A, int t) {
   }
 }
 
+// the same with one THREAD per query (most points of the target frame have no moved anchor point near them)
+__global__ void __launch_bounds__(256) trk_extract_thread_kernel(Trk A, int t) {
+  const int total = A.eoff[A.J];
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += stride) {
+    const int j = seg_of_item(A.eoff, A.J, (int)w);
+    const int i = (int)w - A.eoff[j];
+    const float4 q = A.seq_sorted[A.frame_off[A.cur_nxt[j]] + i];
+    const unsigned long long k = nn_search_thread(A.eg, true, j, q.y, q.z, q.w, 0.f, A.nn_r2, 0u);
+    int out = -1;
+    if (k != ~0ull) {
+      const int g = A.m_gid[(int)(unsigned int)(k & 0xffffffffu)];
+      if (!A.g_stopped[g]) out = g;
+    }
+    A.ex[A.exoff[(long long)j * kRelFrames + t] + i] = out;
+  }
+}
+
 __global__ void __launch_bounds__(256) trk_eg_clear_kernel(Trk A) {
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   pg_clear_used(A.eg, tid, (long long)gridDim.x * blockDim.x);
@@ -2316,7 +2334,15 @@ int pcs_trk_step(pcs_stream_t s, const pcs_trk_ctx_t *C, const pcs_trk_sampler_t
   PCS_LAUNCH(trk_shift_count_kernel, blocks_for(A.M, 256), 256, 0, st, A, t);
   PCS_LAUNCH(trk_eg_ranges_kernel, grid_for(A.M, 256, 4), 256, 0, st, A);
   PCS_LAUNCH(trk_eg_scatter_kernel, blocks_for(A.M, 256), 256, 0, st, A);
-  PCS_LAUNCH(trk_extract_kernel, 148 * 8, 256, 0, st, A, t);
+  static int warp_mode = -1;
+  if (warp_mode < 0) {
+    const char *e = getenv("PCS_GSEARCH_WARP");
+    warp_mode = (e && atoi(e)) ? 1 : 0;
+  }
+  if (warp_mode)
+    PCS_LAUNCH(trk_extract_kernel, 148 * 8, 256, 0, st, A, t);
+  else
+    PCS_LAUNCH(trk_extract_thread_kernel, 148 * 8, 256, 0, st, A, t);
   PCS_LAUNCH(trk_eg_clear_kernel, grid_for(A.M, 256, 4), 256, 0, st, A);
   return 0;
 }
