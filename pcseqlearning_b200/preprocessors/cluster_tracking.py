@@ -536,12 +536,14 @@ class ClusterTracking(nn.Module):
             g0, g1 = tb.inst_goff_h[j], tb.inst_goff_h[j + 1]
             loc = tb.g_local[g0:g1]
             Cx = int(tb.flat_cmax[j]) + 1
-            hit = torch.zeros(Cx, dtype=torch.long, device=dev)
-            size = torch.ones(Cx, dtype=torch.long, device=dev)
-            inr = loc < Cx
-            hit[loc[inr]] = g_hit[g0:g1][inr]
-            size[loc[inr]] = g_size[g0:g1][inr]
-            fe.component_hit, fe.component_size = hit, size
+            # components beyond the largest extracted id go to a dump slot (no boolean-mask indexing: that is a
+            # device->host sync per instance)
+            hit = torch.zeros(Cx + 1, dtype=torch.long, device=dev)
+            size = torch.ones(Cx + 1, dtype=torch.long, device=dev)
+            li = torch.clamp(loc, max=Cx)
+            hit[li] = torch.where(loc < Cx, g_hit[g0:g1], torch.zeros_like(li))
+            size[li] = torch.where(loc < Cx, g_size[g0:g1], torch.ones_like(li))
+            fe.component_hit, fe.component_size = hit[:Cx], size[:Cx]
             out[j] = fe
         return out
 
