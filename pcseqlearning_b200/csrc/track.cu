@@ -8,10 +8,11 @@
 // instances) is ONE batch:
 //   * trk_sample_*      voxel down-sampling of all moving clouds at once (sample_frame, cluster_tracking.py:39-51):
 //                       per-instance grid origin, fp64 means, majority `stationary`, upper-median component
-//   * trk_icp_kernel    ONE persistent cooperative launch per level for all instances: per-iteration moving-grid
-//                       rebuild, two-way K=1 nearest-neighbour search, fp64 raw-moment reductions (register-resident
-//                       per warp, flushed on component change), Jacobi 3x3 SVD rotation, regulariser, and the
-//                       reference's loss-based 3-strike stopping rule evaluated per instance on the device
+//   * trk_icp_kernel    ONE persistent cooperative launch per level for all instances (one 1024-thread CTA per SM):
+//                       per-iteration moving-grid rebuild, two-way K=1 nearest-neighbour search over work lists
+//                       handed out by a work counter, exact neighbour caching, fp64 raw-moment reductions (segmented
+//                       warp sums per component), Jacobi 3x3 SVD rotation, regulariser, and the reference's
+//                       loss-based 3-strike stopping rule evaluated per instance on the device
 //   * trk_smooth_kernel AdamW velocity smoothing (smooth_velo, :162-199), one thread-block cluster per instance
 //   * trk_update / trk_extract  stopping tests (:675-691) and nearest-neighbour point extraction (:710-721)
 // No host synchronisation happens between the first and the last step of a sequence.
@@ -1019,9 +1020,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) trk_icp_kernel(IcpB A) {
     grid.sync();
     ICP_PROF(2)
     // ---- E: both nearest-neighbour searches + raw moments of the edge set -------------------------------------
-    // One work item per lane.  A query whose neighbour of the previous iteration is still within one cell is
-    // settled by its own thread (27 fine cells, bound = that distance: exact); the others -- first iteration, lost
-    // or far neighbours -- are searched by the whole warp, one after the other, over the 5x5x5 block.
+    // One work item per lane.  A query whose cached neighbour is provably still the nearest (distance bounds, see
+    // below) is settled by its own lane; the others are searched by the whole warp, one after the other, over the 27
+    // cells around the query, seeded with the previous neighbour.
     // active work items of this iteration: [forward voxels | backward reference voxels] of every running instance
     // (every thread loads one instance -- the barrier before this phase invalidated L1, a serial loop of one thread
     // over the instances would be a chain of L2 round trips with the rest of the CTA waiting)
